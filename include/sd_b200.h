@@ -1,0 +1,185 @@
+/*
+ * sd_b200.h -- C ABI of the B200-native BrainEncoder + CLIPLoss hot path.
+ *
+ * The reference (SeanNobel/speech-decoding) is pure Python/PyTorch and has no
+ * FFI of its own; the interface each entry point replaces is therefore a
+ * PyTorch call site in the reference, cited as file:line under
+ * /root/reference/.  The Python drop-in (speech-decoding_b200/speech_decoding)
+ * binds these with ctypes.
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, a CUDA stream as void*.
+ *   - every function returns 0 on success, non-zero on failure;
+ *     sd_last_error() returns a thread-local message for the last failure.
+ *   - all launches are asynchronous on `stream`; nothing synchronises.
+ *   - the library never allocates device memory that outlives a call; the
+ *     caller (PyTorch's caching allocator) owns every buffer.
+ *   - re-entrant: forward runs on the main thread, backward on autograd's
+ *     worker thread.
+ *
+ * Internal activation layout ("BTC"): (B, T, Cp) channels-last, Cp = C rounded
+ * up to a multiple of 8, pad channels hold zeros.  dtype is SD_F32 or SD_BF16.
+ * Packed weights: forward layout wf (G, taps, Np, Kp) and data-gradient layout
+ * wd (G, taps, Kp, Np) with the taps reversed; both K-major for the MMA.
+ */
+#ifndef SD_B200_H
+#define SD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_F32 0
+#define SD_BF16 1
+
+#define SD_ACT_NONE 0
+#define SD_ACT_GELU 1 /* out = gelu(p); p optionally saved to `preact`           (models.py:194-195) */
+#define SD_ACT_GLU 2  /* out[:, c] = p[:, c] * sigmoid(p[:, D2 + c]); p saved     (models.py:164)     */
+
+#define SD_OUT_BTC 0     /* (B, T, Np) in `dtype`                                                      */
+#define SD_OUT_NCT_F32 1 /* (B, N, T) fp32 contiguous: the module-facing layout of Z (models.py:195)   */
+
+#define SD_IMPL_AUTO 0
+#define SD_IMPL_SIMT 1 /* fp32-accumulate CUDA-core kernels (any dtype)                                */
+#define SD_IMPL_TC 2   /* tcgen05/TMEM/TMA kernels (bf16)                                              */
+
+const char* sd_last_error(void);
+int sd_abi_version(void);
+/* sm count and compute capability of the current device */
+int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* force a kernel family for conv/wgrad (tests compare TC against SIMT); default SD_IMPL_AUTO */
+int sd_set_impl(int impl);
+
+/* ---- layout conversion ------------------------------------------------------------------------ */
+/* X (B,C,T) fp32 -> (B,T,Cp) dtype, zero padded.  Replaces the implicit layout of
+ * einsum("oi,bit->bot") operands, models.py:65. */
+int sd_nct_to_btc(const float* x, void* out, int B, int C, int T, int Cp, int dtype, void* stream);
+/* (B,T,Cp) dtype -> (B,C,T) fp32 (module-facing outputs / gradients of standalone sub-modules) */
+int sd_btc_to_nct(const void* in, float* out, int B, int C, int T, int Cp, int dtype, void* stream);
+
+/* One weight (N, K, taps) fp32 in PyTorch Conv1d layout (models.py:97-109,128-150,188-189)
+ * -> wf (taps, Np, Kp) and wd (taps, Kp, Np) with reversed taps, zero padded, in `dtype`.
+ * Either destination may be NULL. */
+int sd_pack_weight(const float* w, void* wf, void* wd, int N, int K, int taps, int Np, int Kp, int dtype,
+                   void* stream);
+/* batched form: `table` is a device array of n entries of sd_pack_entry */
+typedef struct {
+  const float* w;
+  void* wf;
+  void* wd;
+  int N, K, taps, Np, Kp, dtype;
+} sd_pack_entry;
+int sd_pack_weights(const sd_pack_entry* table, int n, void* stream);
+
+/* ---- SpatialAttention (models.py:45-65) + SpatialDropout (models.py:77-86) -------------------- */
+/* a = Re(z)·cos + Im(z)·sin (models.py:49-53); w = softmax(a, -1) (:58); masked w·mask is what the
+ * channel mix uses (dropping input channels == zeroing weight columns).
+ *   z_ri (D1,K2,2) interleaved re/im; cos,sin (K2,C); mask (C) or NULL (eval)
+ *   w_soft (D1,C) fp32 saved for backward; w_packed (1,D1p,Cp) `dtype` for sd_conv_fwd. */
+int sd_sa_weights_fwd(const float* z_ri, const float* cos_t, const float* sin_t, const float* mask,
+                      float* w_soft, void* w_packed, int D1, int K2, int C, int D1p, int Cp, int dtype,
+                      void* stream);
+/* dwm (D1,C) fp32 = gradient w.r.t. the masked mixing weights; dz_ri (D1,K2,2) = z.grad
+ * (autograd convention dL/dRe + i dL/dIm). */
+int sd_sa_weights_bwd(const float* dwm, const float* w_soft, const float* mask, const float* cos_t,
+                      const float* sin_t, float* dz_ri, int D1, int K2, int C, void* stream);
+
+/* ---- implicit-GEMM Conv1d: forward and data-gradient ------------------------------------------ */
+/* out[b,t,n] = act( bias[n] + res[b,t,n] + sum_j sum_k in[b, t+(j-(taps-1)/2)*dil, k] * w[g(b),j,n,k] )
+ * zero outside [0,T) ("same" padding, models.py:128-150).  With taps=1 this is the 1x1 convs
+ * (models.py:97,188-189), the channel mix (models.py:65) and, with widx, the per-subject layer
+ * (models.py:98-116, a grouped GEMM indexed by subject id).  dgrad is the same op on wd. */
+typedef struct {
+  const void* in;    /* (B,T,Kp) dtype                                      */
+  const void* w;     /* (G,taps,Np,Kp) dtype                                */
+  const float* bias; /* (N) fp32 or NULL                                    */
+  const void* res;   /* (B,T,Np) dtype or NULL: residual add (models.py:156,160) */
+  const int* widx;   /* (B) int32 group per sample, or NULL (G = 1)         */
+  void* out;         /* see out_mode; with SD_ACT_GLU: (B,T,Op), Op = roundup8(N/2) */
+  void* preact;      /* (B,T,Np) dtype or NULL: pre-activation, saved for backward */
+  double* stats;     /* (2,Np) or NULL: += per-channel sum and sum of squares of the stored
+                        pre-BN output (nn.BatchNorm1d batch statistics, models.py:135,143) */
+  float* rownorm2;   /* (B) or NULL: += sum over (n,t) of out^2 per sample (CLIP norm, loss.py:65) */
+  int B, T, K, Kp, N, Np, taps, dil, G;
+  int act, out_mode, dtype;
+} sd_conv_args;
+int sd_conv_fwd(const sd_conv_args* a, void* stream);
+
+/* ---- Conv1d weight/bias gradient ----------------------------------------------------------------
+ * dw[g, n, k, j] += sum_{b in group g} sum_t dout[b,t,n] * in[b, t+(j-(taps-1)/2)*dil, k]
+ * written with element strides (gs, sn, sk, sj) so it lands in PyTorch's (N,K,taps) layout;
+ * dbias[n] += sum_{b,t} dout[b,t,n].  Caller zeroes dw/dbias.  Groups: samples sorted by subject. */
+typedef struct {
+  const void* dout;         /* (B,T,Np) dtype */
+  const void* in;           /* (B,T,Kp) dtype */
+  float* dw;
+  float* dbias;             /* (N) or NULL */
+  const int* sample_order;  /* (B) int32: sample indices sorted by group, or NULL (identity) */
+  const int* group_offsets; /* (G+1) int32 offsets into sample_order, or NULL (G = 1) */
+  int B, T, K, Kp, N, Np, taps, dil, G;
+  int64_t gs, sn, sk, sj;
+  int dtype;
+} sd_wgrad_args;
+int sd_conv_wgrad(const sd_wgrad_args* a, void* stream);
+
+/* ---- BatchNorm1d + GELU (models.py:158,161) ----------------------------------------------------- */
+/* column sums over a (rows, Cp) BTC tensor: stats[0:Cp] += sum, stats[Cp:2Cp] += sum of squares */
+int sd_colstats(const void* x, double* stats, int64_t rows, int Cp, int dtype, void* stream);
+/* training: mean/var from stats, running-stat update (momentum, unbiased var), num_batches_tracked += 1.
+ * eval: use running stats.  ss (4,Cp) fp32 = scale, shift, mean, invstd. */
+int sd_bn_finalize(const double* stats, int C, int Cp, int64_t n, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                   float eps, int training, float* ss, void* stream);
+/* u = gelu(y*scale + shift) */
+int sd_bn_gelu_fwd(const void* y, const float* ss, void* u, int64_t rows, int Cp, int dtype, void* stream);
+/* g = du * gelu'(y*scale+shift) written in place over du; red (2,Cp) += sum g, sum g*xhat */
+int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* red, int64_t rows, int Cp,
+                          int dtype, void* stream);
+/* dy = scale*(g - sum_g/n - xhat*sum_gx/n) in place over g; also dgamma = sum_gx, dbeta = sum_g (C).
+ * n = n_stat = number of rows the statistics cover (rows * world size under SyncBN).
+ * eval-mode BN (training=0): dy = scale*g. */
+int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* red, float* dgamma,
+                    float* dbeta, int64_t rows, int64_t n_stat, int C, int Cp, int training, int dtype,
+                    void* stream);
+
+/* ---- GLU (models.py:164) and GELU backward ------------------------------------------------------- */
+int sd_glu_fwd(const void* y2, void* out, int64_t rows, int D2, int Np, int Op, int dtype, void* stream);
+int sd_glu_bwd(const void* dout, const void* y2, void* dy2, int64_t rows, int D2, int Np, int Op, int dtype,
+               void* stream);
+/* dp = du * gelu'(p), in place over du; (rows,Cp) BTC */
+int sd_gelu_bwd(void* du_dp, const void* p, int64_t rows, int Cp, int dtype, void* stream);
+/* dZ (B,N,T) fp32 NCT, p (B,T,Np) -> dp (B,T,Np) = dZ^T * gelu'(p) */
+int sd_gelu_bwd_nct(const float* dz, const void* p, void* dp, int B, int N, int T, int Np, int dtype,
+                    void* stream);
+
+/* ---- CLIPLoss (loss.py:38-84) --------------------------------------------------------------------- */
+/* nrm2[i] = sum_d x[i,d]^2  (x (M,D) fp32) */
+int sd_rownorm2(const float* x, float* nrm2, int M, int64_t D, void* stream);
+/* dots[i,j] += sum_d x[i,d] * z[j,d]   (x (M,D), z (N,D) fp32; dots (M,N) fp32, caller zeroes):
+ * the similarity GEMM torch.matmul(x, y.T), loss.py:68, on un-normalised rows. */
+int sd_clip_dots(const float* x, const float* z, float* dots, int M, int N, int64_t D, void* stream);
+/* Phase 1: logits[i,j] = exp(temp) * dots[i,j] / (|x_i||z_j|)  (loss.py:64-71);
+ *   row_stat (M,2) = (max_j, sum_j exp(l - max)) over the local columns,
+ *   col_lse (N)    = logsumexp_i (all M rows are local to every rank).
+ * Multi-GPU: x holds the global batch (M rows), z the local shard (N columns); the caller
+ * all-reduces row_stat across ranks between phase 1 and phase 2. */
+int sd_clip_phase1(const float* dots, const float* xn2, const float* zn2, const float* temp, float* logits,
+                   float* row_stat, float* col_lse, int M, int N, void* stream);
+/* Phase 2: with row_lse (M) global,
+ *   G = d loss / d logits = scale/2 * (softmax_rows + softmax_cols - 2*I), I at (diag0 + j, j)
+ *   coef[i,j] = exp(temp) * G[i,j] / (|x_i||z_j|);  cz[j] = (sum_i G*logits)[j] / |z_j|^2
+ *   partial[0] += this rank's share of the loss, partial[1] += sum G*logits (= d loss / d temp)
+ *   scale = 1/M_global for reduction="mean", 1 for "sum" (loss.py:32,79). */
+int sd_clip_phase2(const float* logits, const float* row_lse, const float* col_lse, const float* xn2,
+                   const float* zn2, const float* temp, float scale, int diag0, float* coef, float* cz,
+                   float* partial, int M, int N, void* stream);
+/* dz[j,d] = sum_i coef[i,j] * x[i,d] - cz[j] * z[j,d]   (appendix A.5) */
+int sd_clip_dz(const float* coef, const float* cz, const float* x, const float* z, float* dz, int M, int N,
+               int64_t D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SD_B200_H */

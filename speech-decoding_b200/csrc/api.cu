@@ -1,0 +1,85 @@
+// C-ABI glue: error reporting, device query, implementation dispatch for the conv family.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace sd {
+
+static thread_local char g_err[512] = "";
+static int g_impl = SD_IMPL_AUTO;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int current_impl() { return g_impl; }
+
+}  // namespace sd
+
+using namespace sd;
+
+extern "C" {
+
+const char* sd_last_error(void) { return g_err; }
+
+int sd_abi_version(void) { return 1; }
+
+int sd_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  SD_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  SD_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return 0;
+}
+
+int sd_set_impl(int impl) {
+  SD_REQUIRE(impl >= SD_IMPL_AUTO && impl <= SD_IMPL_TC, "sd_set_impl: bad value %d", impl);
+  g_impl = impl;
+  return 0;
+}
+
+int sd_conv_fwd(const sd_conv_args* a, void* stream) {
+  SD_REQUIRE(a != nullptr, "sd_conv_fwd: null args");
+  SD_REQUIRE(a->taps == 1 || a->taps == 3, "sd_conv_fwd: taps must be 1 or 3 (got %d)", a->taps);
+  SD_REQUIRE(a->Kp % 8 == 0 && a->Np % 8 == 0, "sd_conv_fwd: padded channel counts must be multiples of 8");
+  SD_REQUIRE(a->dtype == SD_F32 || a->dtype == SD_BF16, "sd_conv_fwd: bad dtype");
+  SD_REQUIRE(a->B > 0 && a->T > 0, "sd_conv_fwd: empty input");
+  const int impl = current_impl();
+  if (impl == SD_IMPL_TC) {
+    SD_REQUIRE(conv_fwd_tc_supported(*a), "sd_conv_fwd: tcgen05 path does not support this configuration");
+    return conv_fwd_tc(*a, (cudaStream_t)stream);
+  }
+  if (impl == SD_IMPL_AUTO && conv_fwd_tc_supported(*a)) return conv_fwd_tc(*a, (cudaStream_t)stream);
+  return conv_fwd_simt(*a, (cudaStream_t)stream);
+}
+
+int sd_conv_wgrad(const sd_wgrad_args* a, void* stream) {
+  SD_REQUIRE(a != nullptr, "sd_conv_wgrad: null args");
+  SD_REQUIRE(a->taps == 1 || a->taps == 3, "sd_conv_wgrad: taps must be 1 or 3");
+  SD_REQUIRE(a->Kp % 8 == 0 && a->Np % 8 == 0, "sd_conv_wgrad: padded channel counts must be multiples of 8");
+  SD_REQUIRE(a->dtype == SD_F32 || a->dtype == SD_BF16, "sd_conv_wgrad: bad dtype");
+  const int impl = current_impl();
+  if (impl == SD_IMPL_TC) {
+    SD_REQUIRE(conv_wgrad_tc_supported(*a), "sd_conv_wgrad: tcgen05 path does not support this configuration");
+    return conv_wgrad_tc(*a, (cudaStream_t)stream);
+  }
+  if (impl == SD_IMPL_AUTO && conv_wgrad_tc_supported(*a)) return conv_wgrad_tc(*a, (cudaStream_t)stream);
+  return conv_wgrad_simt(*a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""Data-parallel plumbing (one process per GPU, torch.distributed over NCCL).
+
+The reference is single-device (train.py:31); batch sharding is this build's
+addition:
+
+  * every rank runs the full encoder on its shard of the batch;
+  * CLIP negatives span the global batch: the speech rows x (input data, no
+    gradient) are all-gathered, each rank scores them against its local brain
+    rows z, column statistics stay local and only the (M,2) row statistics
+    (max, sum-exp) and two scalars cross ranks -- no gradient exchange for dz;
+  * parameter gradients are summed across ranks (the loss is the global-batch
+    loss, so SUM, not average), launched per stage from inside backward so the
+    all-reduce overlaps the remaining backward kernels;
+  * optional SyncBN (per-channel statistics all-reduced) so the result equals
+    the single-process run on the concatenated batch;
+  * subject presence (which per-subject weights receive a gradient at all) is
+    agreed on the host over a gloo side-channel, so no device sync is needed.
+
+Everything here is host logic over torch.distributed and runs unchanged on the
+gloo backend with CPU tensors (tests/test_dist_cpu.py).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world_rank(group=None):
+    if group is None or not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def all_gather_rows(x, group):
+    world, _ = world_rank(group)
+    if world == 1:
+        return x
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def all_reduce_sum(t, group):
+    t = t.contiguous()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def merge_row_stats(row_stat, group):
+    """(M,2) per-rank (max_j, sum_j exp(l - max)) over local columns ->
+    the same statistics over the columns of all ranks."""
+    m_local = row_stat[:, 0].contiguous()
+    m_glob = m_local.clone()
+    dist.all_reduce(m_glob, op=dist.ReduceOp.MAX, group=group)
+    s = (row_stat[:, 1] * torch.exp(m_local - m_glob)).contiguous()
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    return torch.stack([m_glob, s], dim=1)
+
+
+def gather_host_ints(values, host_group):
+    """all-gather a small int64 numpy vector over the host (gloo) side channel."""
+    world, _ = world_rank(host_group)
+    t = torch.from_numpy(np.asarray(values, dtype=np.int64))
+    if world == 1:
+        return [t.numpy()]
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=host_group)
+    return [o.numpy() for o in outs]
+
+
+class GradReducer:
+    """Sums parameter gradients across ranks, stage by stage, while backward
+    is still running (hooked into engine.Pipeline)."""
+
+    def __init__(self, group):
+        self.group = group
+        self.pending = []
+
+    def stage_done(self, grads):
+        """grads: {param: tensor} produced by one stage.  Launch one coalesced
+        asynchronous all-reduce for them."""
+        tensors = [g for g in grads.values() if g is not None]
+        if not tensors:
+            return
+        flat = torch.cat([torch.view_as_real(t).reshape(-1) if t.is_complex() else t.reshape(-1) for t in tensors])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.pending.append((work, flat, tensors))
+
+    def finish(self):
+        for work, flat, tensors in self.pending:
+            work.wait()
+            off = 0
+            for t in tensors:
+                v = torch.view_as_real(t) if t.is_complex() else t
+                n = v.numel()
+                v.copy_(flat[off:off + n].view_as(v))
+                off += n
+        self.pending = []
+
+
+class DataParallel:
+    """Wire a BrainEncoder + CLIPLoss pair for batch-sharded training.
+
+        dp = DataParallel(encoder, loss_fn, group=None, sync_bn=True)
+        Z = encoder(X_local, ids_local); loss = loss_fn(Y_local, Z); loss.backward()
+
+    `loss` is the global-batch loss on every rank; parameter .grad's are the
+    global-batch gradients (identical on every rank)."""
+
+    def __init__(self, encoder, loss_fn, group=None, sync_bn=True, host_group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group if group is not None else dist.group.WORLD
+        self.host_group = host_group
+        if host_group is None and dist.get_backend(self.group) != "gloo":
+            self.host_group = dist.new_group(backend="gloo")
+        elif host_group is None:
+            self.host_group = self.group
+        pipe = encoder.pipeline()
+        pipe.reducer = GradReducer(self.group)
+        pipe.bn_group = self.group if sync_bn else None
+        pipe.host_group = self.host_group
+        loss_fn.process_group = self.group
+        self.temp_reducer = loss_fn
+        # the temperature gradient is a partial sum per rank: the loss Function already
+        # all-reduces `partial`, so dtemp is global -- nothing more to do for it.

@@ -1,0 +1,201 @@
+"""Thin tensor-level wrappers over the C ABI (include/sd_b200.h).  PyTorch is
+used only for device memory, streams and the autograd graph edge; every
+computation below is a launch into libsd_b200.so."""
+import os
+
+import torch
+
+from . import _native as nat
+
+_PRECISIONS = {"fp32": (torch.float32, nat.SD_F32), "bf16": (torch.bfloat16, nat.SD_BF16)}
+_precision = os.environ.get("SD_B200_PRECISION", "bf16")
+
+
+def set_precision(p: str):
+    """'bf16' (default; bf16 activations/weight shadows, fp32 accumulate and
+    master parameters) or 'fp32' (fp32 everywhere; exact-parity mode)."""
+    global _precision
+    if p not in _PRECISIONS:
+        raise ValueError("precision must be one of %s" % list(_PRECISIONS))
+    _precision = p
+
+
+def get_precision() -> str:
+    return _precision
+
+
+def dtypes(precision=None):
+    return _PRECISIONS[precision or _precision]
+
+
+def set_impl(name: str):
+    """'auto' | 'simt' | 'tc' -- kernel family for conv / wgrad (tests)."""
+    nat.call("sd_set_impl", {"auto": nat.IMPL_AUTO, "simt": nat.IMPL_SIMT, "tc": nat.IMPL_TC}[name])
+
+
+def rup8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("sd_b200: %s must be a CUDA tensor -- this implementation has no CPU path "
+                           "(got device=%s)" % (name, t.device))
+
+
+def code_of(t):
+    if t.dtype == torch.float32:
+        return nat.SD_F32
+    if t.dtype == torch.bfloat16:
+        return nat.SD_BF16
+    raise RuntimeError("sd_b200: unsupported activation dtype %s" % t.dtype)
+
+
+# ---- layout -------------------------------------------------------------------------------------
+def nct_to_btc(x, dtype):
+    B, C, T = x.shape
+    Cp = rup8(C)
+    out = torch.empty((B, T, Cp), dtype=dtype, device=x.device)
+    nat.call("sd_nct_to_btc", _p(x), _p(out), B, C, T, Cp, code_of(out), _st())
+    return out
+
+
+def btc_to_nct(a, C):
+    B, T, Cp = a.shape
+    out = torch.empty((B, C, T), dtype=torch.float32, device=a.device)
+    nat.call("sd_btc_to_nct", _p(a), _p(out), B, C, T, Cp, code_of(a), _st())
+    return out
+
+
+# ---- conv ----------------------------------------------------------------------------------------
+def conv_fwd(inp, w, *, K, N, taps=1, dil=1, bias=None, res=None, widx=None, G=1, out=None, preact=None,
+             stats=None, rownorm2=None, act=nat.ACT_NONE, out_mode=nat.OUT_BTC):
+    B, T, Kp = inp.shape
+    Np = rup8(N)
+    a = nat.ConvArgs(_p(inp), _p(w), _p(bias), _p(res), _p(widx), _p(out), _p(preact), _p(stats), _p(rownorm2),
+                     B, T, K, Kp, N, Np, taps, dil, G, act, out_mode, code_of(inp))
+    nat.call("sd_conv_fwd", a, _st())
+    return out
+
+
+def conv_wgrad(dout, inp, dw, *, K, N, taps=1, dil=1, dbias=None, order=None, offsets=None, G=1,
+               strides=None):
+    B, T, Np = dout.shape
+    Kp = inp.shape[2]
+    if strides is None:                      # PyTorch Conv1d weight (N, K, taps)
+        strides = (N * K * taps, K * taps, taps, 1)
+    a = nat.WgradArgs(_p(dout), _p(inp), _p(dw), _p(dbias), _p(order), _p(offsets),
+                      B, T, K, Kp, N, Np, taps, dil, G, strides[0], strides[1], strides[2], strides[3],
+                      code_of(dout))
+    nat.call("sd_conv_wgrad", a, _st())
+
+
+# ---- batchnorm / gelu / glu ---------------------------------------------------------------------
+def bn_finalize(stats, C, Cp, n, gamma, beta, rmean, rvar, nbt, momentum, eps, training, ss):
+    nat.call("sd_bn_finalize", _p(stats), C, Cp, n, _p(gamma), _p(beta), _p(rmean), _p(rvar), _p(nbt),
+             momentum, eps, int(training), _p(ss), _st())
+
+
+def bn_gelu_fwd(y, ss, u):
+    rows = y.shape[0] * y.shape[1]
+    nat.call("sd_bn_gelu_fwd", _p(y), _p(ss), _p(u), rows, y.shape[2], code_of(y), _st())
+
+
+def bn_gelu_bwd(du, y, ss, red, dgamma, dbeta, C, training, group=None):
+    """in place: du -> dy (gradient w.r.t. the pre-BN tensor y).  With `group`
+    (SyncBN) the two per-channel sums are all-reduced between the passes."""
+    rows, Cp = y.shape[0] * y.shape[1], y.shape[2]
+    n_stat = rows
+    nat.call("sd_bn_gelu_bwd_reduce", _p(du), _p(y), _p(ss), _p(red), rows, Cp, code_of(y), _st())
+    if group is not None and training:
+        import torch.distributed as dist
+        dist.all_reduce(red, group=group)
+        n_stat = rows * dist.get_world_size(group)
+    nat.call("sd_bn_bwd_apply", _p(du), _p(y), _p(ss), _p(red), _p(dgamma), _p(dbeta), rows, n_stat, C, Cp,
+             int(training), code_of(y), _st())
+
+
+def glu_bwd(dout, y2, dy2, D2):
+    rows = y2.shape[0] * y2.shape[1]
+    nat.call("sd_glu_bwd", _p(dout), _p(y2), _p(dy2), rows, D2, y2.shape[2], dout.shape[2], code_of(y2), _st())
+
+
+def gelu_bwd(du, p):
+    rows = p.shape[0] * p.shape[1]
+    nat.call("sd_gelu_bwd", _p(du), _p(p), rows, p.shape[2], code_of(p), _st())
+
+
+def gelu_bwd_nct(dz, p, N):
+    B, T, Np = p.shape
+    dp = torch.empty_like(p)
+    nat.call("sd_gelu_bwd_nct", _p(dz), _p(p), _p(dp), B, N, T, Np, code_of(p), _st())
+    return dp
+
+
+# ---- spatial attention --------------------------------------------------------------------------
+def sa_weights_fwd(z_ri, cos, sin, mask, D1, K2, C, dtype):
+    D1p, Cp = rup8(D1), rup8(C)
+    w_soft = torch.empty((D1, C), dtype=torch.float32, device=z_ri.device)
+    w_packed = torch.empty((1, 1, D1p, Cp), dtype=dtype, device=z_ri.device)
+    nat.call("sd_sa_weights_fwd", _p(z_ri), _p(cos), _p(sin), _p(mask), _p(w_soft), _p(w_packed),
+             D1, K2, C, D1p, Cp, code_of(w_packed), _st())
+    return w_soft, w_packed
+
+
+def sa_weights_bwd(dwm, w_soft, mask, cos, sin, K2):
+    D1, C = w_soft.shape
+    dz = torch.empty((D1, K2, 2), dtype=torch.float32, device=dwm.device)
+    nat.call("sd_sa_weights_bwd", _p(dwm), _p(w_soft), _p(mask), _p(cos), _p(sin), _p(dz), D1, K2, C, _st())
+    return dz
+
+
+# ---- CLIP -----------------------------------------------------------------------------------------
+def rownorm2(x2d):
+    M, D = x2d.shape
+    out = torch.empty((M,), dtype=torch.float32, device=x2d.device)
+    nat.call("sd_rownorm2", _p(x2d), _p(out), M, D, _st())
+    return out
+
+
+def clip_dots(x2d, z2d):
+    M, D = x2d.shape
+    Nn = z2d.shape[0]
+    dots = torch.zeros((M, Nn), dtype=torch.float32, device=x2d.device)
+    nat.call("sd_clip_dots", _p(x2d), _p(z2d), _p(dots), M, Nn, D, _st())
+    return dots
+
+
+def clip_phase1(dots, xn2, zn2, temp):
+    M, Nn = dots.shape
+    logits = torch.empty_like(dots)
+    row_stat = torch.empty((M, 2), dtype=torch.float32, device=dots.device)
+    col_lse = torch.empty((Nn,), dtype=torch.float32, device=dots.device)
+    nat.call("sd_clip_phase1", _p(dots), _p(xn2), _p(zn2), _p(temp), _p(logits), _p(row_stat), _p(col_lse),
+             M, Nn, _st())
+    return logits, row_stat, col_lse
+
+
+def clip_phase2(logits, row_lse, col_lse, xn2, zn2, temp, scale, diag0):
+    M, Nn = logits.shape
+    coef = torch.empty_like(logits)
+    cz = torch.empty((Nn,), dtype=torch.float32, device=logits.device)
+    partial = torch.empty((2,), dtype=torch.float32, device=logits.device)
+    nat.call("sd_clip_phase2", _p(logits), _p(row_lse), _p(col_lse), _p(xn2), _p(zn2), _p(temp), scale, diag0,
+             _p(coef), _p(cz), _p(partial), M, Nn, _st())
+    return coef, cz, partial
+
+
+def clip_dz(coef, cz, x2d, z2d):
+    M, D = x2d.shape
+    Nn = z2d.shape[0]
+    dz = torch.empty((Nn, D), dtype=torch.float32, device=x2d.device)
+    nat.call("sd_clip_dz", _p(coef), _p(cz), _p(x2d), _p(z2d), _p(dz), M, Nn, D, _st())
+    return dz

