@@ -1,9 +1,457 @@
-// tcgen05 / TMEM / TMA implicit-GEMM Conv1d family (bf16) -- placeholder until the kernels land.
-#include "common.cuh"
+// tcgen05 / TMEM / TMA implicit-GEMM Conv1d (bf16 operands, fp32 accumulation in tensor memory).
+//
+// Reference semantics: nn.Conv1d(k in {1,3}, padding="same", dilation) + bias (+ residual) of
+// speech_decoding/models.py:97-109,128-150,156,160,188-189 with the BatchNorm batch statistics
+// (models.py:158,161), GELU (models.py:194-195) and GLU (models.py:164) fused into the epilogue.
+//
+// GEMM view per CTA tile:  D[128 time rows, BLOCK_N channels] = sum_{tap j} sum_{k-block}
+//     A_j[128 x 64] (activations, rows t0+shift_j.., channels-last => K-major, 3-D TMA box whose
+//                    out-of-range rows are zero-filled: that *is* the "same" padding and it never
+//                    bleeds into the neighbouring sample)
+//   x W_j[BLOCK_N x 64]^T (packed weights (G,taps,Np,Kp), K-major; the group g is the subject id)
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
+// allocator, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  4-stage smem ring,
+// accumulators double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Persistent grid: one CTA per SM looping over tiles, n-tiles of the same rows adjacent in time
+// so the activation slab is re-read from L2, not HBM.
+#include "tc_common.cuh"
 
 namespace sd {
-bool conv_fwd_tc_supported(const sd_conv_args&) { return false; }
+
+using namespace tc;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int STAGES = 4;
+constexpr int MAX_BLOCK_N = 256;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
+constexpr int B_BYTES = MAX_BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 192;
+
+struct FwdParams {
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* out_btc;
+  float* out_nct;
+  __nv_bfloat16* preact;
+  double* stats;
+  float* rownorm2;
+  const int* widx;
+  int B, T, N, Np, Kp, taps, dil;
+  int block_n, n_tiles, m_tiles_per_sample, num_tiles, k_blocks;
+  int act, out_mode, D2, Op;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// column sums of a 32-row x 16-column register tile held one row per lane: 16 shuffles.
+// On return every lane holds the sum of column `col_of_lane(lane)` over the warp's 32 rows.
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float send = hi ? v[i] : v[i + 8];
+      float keep = hi ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float send = hi ? v[i] : v[i + 4];
+      float keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float send = hi ? v[i] : v[i + 2];
+      float keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool hi = lane & 2;
+    float send = hi ? v[0] : v[1];
+    float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+__device__ __forceinline__ int col_of_lane(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float (&v)[16], int n_base, int limit) {
+  if (n_base + 8 <= limit) {
+    uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dst) = q;
+  }
+  if (n_base + 16 <= limit) {
+    uint4 q = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    *reinterpret_cast<uint4*>(dst + 8) = q;
+  }
+}
+
+__device__ __forceinline__ void load16_bf16_add(const __nv_bfloat16* src, float (&v)[16], int n_base, int limit) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (n_base + 8 * (h + 1) <= limit) {
+      uint4 q = *reinterpret_cast<const uint4*>(src + 8 * h);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+        float2 f = __bfloat1622float2(p);
+        v[8 * h + 2 * i] += f.x;
+        v[8 * h + 2 * i + 1] += f.y;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                   const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  const int k_iters = p.taps * p.k_blocks;
+  const int half_n = p.block_n >> 1;
+  const bool glu = p.act == SD_ACT_GLU;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t stage_tx = A_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
+        const int b = m_idx / p.m_tiles_per_sample;
+        const int t0 = (m_idx % p.m_tiles_per_sample) * BLOCK_M;
+        const int g = p.widx ? __ldg(p.widx + b) : 0;
+        const int row0 = glu ? n_idx * half_n : n_idx * p.block_n;
+        const int row1 = glu ? p.D2 + n_idx * half_n : row0 + half_n;
+        for (int j = 0; j < p.taps; ++j) {
+          const int shift = (j - (p.taps - 1) / 2) * p.dil;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+            mbar_arrive_expect_tx(full_bar(s), stage_tx);
+            tma_load_3d(sa, &tmap_a, full_bar(s), kb * BLOCK_K, t0 + shift, b);
+            tma_load_3d(sb, &tmap_w, full_bar(s), kb * BLOCK_K, row0, g * p.taps + j);
+            tma_load_3d(sb + half_n * (BLOCK_K * 2), &tmap_w, full_bar(s), kb * BLOCK_K, row1, g * p.taps + j);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, BLOCK_M, (uint32_t)p.block_n);
+      int s = 0;
+      uint32_t ph = 0;
+      int it_tile = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
+        const int acc = it_tile & 1;
+        const uint32_t acc_ph = (it_tile >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * MAX_BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024);
+            umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0);
+          }
+          umma_commit(empty_bar(s));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    int it_tile = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
+      const int acc = it_tile & 1;
+      const uint32_t acc_ph = (it_tile >> 1) & 1;
+      const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
+      const int b = m_idx / p.m_tiles_per_sample;
+      const int t = (m_idx % p.m_tiles_per_sample) * BLOCK_M + row;
+      const bool valid = t < p.T;
+      const size_t grow = (size_t)b * p.T + (valid ? t : 0);
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * MAX_BLOCK_N;
+      float sumsq = 0.f;
+
+      if (!glu) {
+        const int n0 = n_idx * p.block_n;
+        for (int cc = 0; cc < p.block_n; cc += 16) {
+          const int nb = n0 + cc;
+          if (nb >= p.Np) break;
+          uint32_t r[16];
+          tmem_ld16(taddr + cc, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = __uint_as_float(r[i]);
+            if (p.bias && nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
+          }
+          if (p.res && valid) load16_bf16_add(p.res + grow * p.Np + nb, v, nb, p.Np);
+          if (p.preact && valid) store16_bf16(p.preact + grow * p.Np + nb, v, nb, p.Np);
+          if (p.act == SD_ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
+          }
+          if (p.out_mode == SD_OUT_BTC) {
+            if (valid) store16_bf16(p.out_btc + grow * p.Np + nb, v, nb, p.Np);
+          } else if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.N) p.out_nct[((size_t)b * p.N + nb + i) * p.T + t] = v[i];
+          }
+          if (p.rownorm2 && valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.N) sumsq += v[i] * v[i];
+          }
+          if (p.stats) {  // statistics of the values as stored (bf16-rounded), invalid rows contribute 0
+            float s1[16], s2[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float q = valid ? bf16_round(v[i]) : 0.f;
+              s1[i] = q;
+              s2[i] = q * q;
+            }
+            float cs = warp_colsum16(s1, lane);
+            float cq = warp_colsum16(s2, lane);
+            const int n = nb + col_of_lane(lane);
+            if ((lane & 1) == 0 && n < p.Np) {
+              atomicAdd(p.stats + n, (double)cs);
+              atomicAdd(p.stats + p.Np + n, (double)cq);
+            }
+          }
+        }
+      } else {
+        // GLU: tile columns [0,half) = a channels c0.., [half, 2*half) = gate channels D2+c0..
+        const int c0 = n_idx * half_n;
+        for (int cc = 0; cc < half_n; cc += 16) {
+          const int cb = c0 + cc;
+          if (cb >= p.Op) break;
+          uint32_t ra[16], rb[16];
+          tmem_ld16(taddr + cc, ra);
+          tmem_ld16(taddr + half_n + cc, rb);
+          tmem_ld_wait();
+          float va[16], vb[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            va[i] = __uint_as_float(ra[i]);
+            vb[i] = __uint_as_float(rb[i]);
+            if (p.bias && cb + i < p.D2) {
+              va[i] += __ldg(p.bias + cb + i);
+              vb[i] += __ldg(p.bias + p.D2 + cb + i);
+            }
+          }
+          if (valid) {
+            if (p.preact) {
+              store16_bf16(p.preact + grow * p.Np + cb, va, cb, p.D2);
+              store16_bf16(p.preact + grow * p.Np + p.D2 + cb, vb, cb, p.D2);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) va[i] = (cb + i < p.D2) ? va[i] * sigmoid_f(vb[i]) : 0.f;
+            store16_bf16(p.out_btc + grow * p.Op + cb, va, cb, p.Op);
+          }
+        }
+      }
+      if (p.rownorm2) {
+        sumsq = warp_sum(sumsq);
+        if (lane == 0) atomicAdd(p.rownorm2 + b, sumsq);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// pick the N tile: multiple of 16, <= 256, minimal padded total, fewest tiles on ties
+int pick_block_n(int n_total) {
+  int best_bn = 16, best_pad = 1 << 30;
+  const int min_tiles = (n_total + MAX_BLOCK_N - 1) / MAX_BLOCK_N;
+  for (int nt = min_tiles; nt <= min_tiles + 3; ++nt) {
+    int bn = ((n_total + nt - 1) / nt + 15) / 16 * 16;
+    if (bn > MAX_BLOCK_N) continue;
+    int pad = bn * nt;
+    if (pad < best_pad) { best_pad = pad; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+namespace tc {
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+  EncodeTiledFn fn = encode_fn();
+  SD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u",
+             (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, box0, box1, box2);
+  return 0;
+}
+
+}  // namespace tc
+
+bool conv_fwd_tc_supported(const sd_conv_args& a) {
+  if (a.dtype != SD_BF16) return false;
+  if (a.act == SD_ACT_GLU && ((a.N / 2) % 8 != 0 || a.out_mode != SD_OUT_BTC || a.N % 2)) return false;
+  if (a.stats && (a.act != SD_ACT_NONE || a.out_mode != SD_OUT_BTC)) return false;
+  if (a.rownorm2 && a.out_mode != SD_OUT_NCT_F32) return false;
+  if (((uintptr_t)a.in & 15) || ((uintptr_t)a.w & 15)) return false;
+  return true;
+}
+
+int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
+  const bool glu = a.act == SD_ACT_GLU;
+  FwdParams p;
+  p.bias = a.bias;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(a.res);
+  p.out_btc = reinterpret_cast<__nv_bfloat16*>(a.out);
+  p.out_nct = reinterpret_cast<float*>(a.out);
+  p.preact = reinterpret_cast<__nv_bfloat16*>(a.preact);
+  p.stats = a.stats;
+  p.rownorm2 = a.rownorm2;
+  p.widx = a.widx;
+  p.B = a.B; p.T = a.T; p.N = a.N; p.Np = a.Np; p.Kp = a.Kp; p.taps = a.taps; p.dil = a.dil;
+  p.act = a.act; p.out_mode = a.out_mode;
+  p.D2 = glu ? a.N / 2 : 0;
+  p.Op = glu ? (p.D2 + 7) / 8 * 8 : 0;
+  if (glu) {
+    const int half = pick_block_n(2 * p.Op) / 2;   // output channels per tile
+    p.block_n = 2 * ((half + 7) / 8 * 8);
+    if (p.block_n % 16) p.block_n += 8;            // keep UMMA_N a multiple of 16 (half stays a multiple of 8)
+    if (p.block_n > MAX_BLOCK_N) p.block_n = MAX_BLOCK_N;
+    p.n_tiles = (p.Op + p.block_n / 2 - 1) / (p.block_n / 2);
+  } else {
+    p.block_n = pick_block_n(a.Np);
+    p.n_tiles = (a.Np + p.block_n - 1) / p.block_n;
+  }
+  p.m_tiles_per_sample = (a.T + BLOCK_M - 1) / BLOCK_M;
+  p.num_tiles = a.B * p.m_tiles_per_sample * p.n_tiles;
+  p.k_blocks = (a.Kp + BLOCK_K - 1) / BLOCK_K;
+
+  CUtensorMap ta, tw;
+  if (make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, (uint64_t)a.Kp, (uint64_t)a.T, (uint64_t)a.B,
+                   (uint64_t)a.Kp * 2, (uint64_t)a.T * a.Kp * 2, BLOCK_K, BLOCK_M, 1))
+    return 1;
+  if (make_tmap_3d(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.w, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.G * a.taps,
+                   (uint64_t)a.Kp * 2, (uint64_t)a.Np * a.Kp * 2, BLOCK_K, (uint32_t)(p.block_n / 2), 1))
+    return 1;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SD_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  conv_fwd_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tw, p);
+  return check_launch("conv_fwd_tc");
+}
+
 bool conv_wgrad_tc_supported(const sd_wgrad_args&) { return false; }
-int conv_fwd_tc(const sd_conv_args&, cudaStream_t) { set_error("tcgen05 conv not built"); return 1; }
-int conv_wgrad_tc(const sd_wgrad_args&, cudaStream_t) { set_error("tcgen05 wgrad not built"); return 1; }
+int conv_wgrad_tc(const sd_wgrad_args&, cudaStream_t) {
+  set_error("tcgen05 wgrad not built");
+  return 1;
+}
+
 }  // namespace sd

@@ -393,6 +393,8 @@ class Pipeline:
         params = self.params()
         for p in params:
             ops.require_cuda(p, "parameter")
+        # grad mode is switched off inside Function.forward, so decide here whether to keep activations
+        self._keep = torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in params))
         return _PipelineFn.apply(self, X, *params)
 
     # called from the autograd node
@@ -424,7 +426,7 @@ class Pipeline:
 class _PipelineFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pipe, X, *params):
-        keep = torch.is_grad_enabled() and (X.requires_grad or any(p.requires_grad for p in params))
+        keep = pipe._keep
         with torch.cuda.device(X.device):
             out, saved = pipe._forward(X, keep)
         ctx.pipe, ctx.saved, ctx.params = pipe, saved, params

@@ -26,3 +26,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_reference():
+    """The PyTorch statements the GPU tests compare against must be true fp32 (cuDNN/cuBLAS default to
+    TF32 for convolutions, which is 1e-3-level noise and would mask real errors)."""
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
+    yield

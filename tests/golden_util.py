@@ -49,3 +49,12 @@ def rel_err(a, b, floor=0.0):
     b = b.detach().double().cpu()
     den = max(float(b.abs().max()), floor, 1e-30)
     return float((a - b).abs().max()) / den
+
+
+def rel_l2(a, b, floor=0.0):
+    """||a-b||_2 / max(||b||_2, floor): the normwise relative error used for the bf16 mode."""
+    a = torch.view_as_real(a) if a.is_complex() else a
+    b = torch.view_as_real(b) if b.is_complex() else b
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm()) / max(float(b.norm()), floor, 1e-30)
