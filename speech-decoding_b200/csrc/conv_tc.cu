@@ -9,11 +9,16 @@
 //                    out-of-range rows are zero-filled: that *is* the "same" padding and it never
 //                    bleeds into the neighbouring sample)
 //   x W_j[BLOCK_N x 64]^T (packed weights (G,taps,Np,Kp), K-major; the group g is the subject id)
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
-// allocator, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  4-stage smem ring,
-// accumulators double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Persistent grid: one CTA per SM looping over tiles, n-tiles of the same rows adjacent in time
-// so the activation slab is re-read from L2, not HBM.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
+// allocator, warps 2..9 = epilogue: two warps per TMEM lane quadrant, each thread owns one output row
+// and half of the tile's columns.  smem ring of TMA stages; accumulators double-buffered in TMEM so
+// the epilogue of tile i overlaps the MMAs of tile i+1.  Epilogue I/O goes through a per-row smem
+// staging line and 1-D bulk copies (cp.async.bulk): the residual row segment is prefetched into the
+// staging line while the MMAs run, the finished row segment leaves as one contiguous bulk store, so
+// global traffic is full-sector both ways and no cross-thread synchronisation is needed.
+// Persistent grid: one CTA per SM looping over tiles, n-tiles of the same rows adjacent in time so
+// the activation slab is re-read from L2, not HBM.
 #include "tc_common.cuh"
 
 namespace sd {
@@ -23,15 +28,14 @@ using namespace tc;
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
-constexpr int STAGES = 4;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int MAX_BLOCK_N = 256;
-constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
-constexpr int B_BYTES = MAX_BLOCK_N * BLOCK_K * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int MAX_STAGES = 6;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct FwdParams {
   const float* bias;
@@ -45,6 +49,8 @@ struct FwdParams {
   int B, T, N, Np, Kp, taps, dil;
   int block_n, n_tiles, m_tiles_per_sample, num_tiles, k_blocks;
   int act, out_mode, D2, Op;
+  // shared-memory plan (byte offsets from the 1024-aligned base)
+  int stages, stage_bytes, pitch, off_stg0, off_stg1, off_bias, off_stats, off_bar, cols_alloc;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -96,61 +102,85 @@ __device__ __forceinline__ int col_of_lane(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
-__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float (&v)[16], int n_base, int limit) {
-  if (n_base + 8 <= limit) {
-    uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(dst) = q;
-  }
-  if (n_base + 16 <= limit) {
-    uint4 q = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-    *reinterpret_cast<uint4*>(dst + 8) = q;
-  }
+// 16 floats -> 16 bf16 (32 B) into shared memory
+__device__ __forceinline__ void sts16_bf16(uint32_t saddr, const float (&v)[16]) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(pack_bf16x2(v[0], v[1])),
+               "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7])) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr + 16), "r"(pack_bf16x2(v[8], v[9])),
+               "r"(pack_bf16x2(v[10], v[11])), "r"(pack_bf16x2(v[12], v[13])), "r"(pack_bf16x2(v[14], v[15])) : "memory");
 }
-
-__device__ __forceinline__ void load16_bf16_add(const __nv_bfloat16* src, float (&v)[16], int n_base, int limit) {
+// v += 16 bf16 read from shared memory
+__device__ __forceinline__ void lds16_bf16_add(uint32_t saddr, float (&v)[16]) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    if (n_base + 8 * (h + 1) <= limit) {
-      uint4 q = *reinterpret_cast<const uint4*>(src + 8 * h);
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t w[4];
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(saddr + 16 * h));
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-        float2 f = __bfloat1622float2(p);
-        v[8 * h + 2 * i] += f.x;
-        v[8 * h + 2 * i + 1] += f.y;
-      }
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 q = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      float2 f = __bfloat1622float2(q);
+      v[8 * h + 2 * i] += f.x;
+      v[8 * h + 2 * i + 1] += f.y;
     }
   }
 }
+__device__ __forceinline__ void lds16_f32_add(uint32_t saddr, float (&v)[16]) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float4 f;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(saddr + 16 * h));
+    v[4 * h] += f.x; v[4 * h + 1] += f.y; v[4 * h + 2] += f.z; v[4 * h + 3] += f.w;
+  }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                    const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
+  const uint32_t bar_base = smem_base + p.off_bar;
+  // barrier layout (8 B each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], res[8], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
+  auto res_bar = [&](int w) { return bar_base + 8u * (2 * MAX_STAGES + 4 + w); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * MAX_STAGES + 4 + NUM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool glu = p.act == SD_ACT_GLU;
+  const int half_n = p.block_n >> 1;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
     }
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 32);
     fence_barrier_init();
+  }
+  // bias (zero beyond N) and statistics accumulators in shared memory
+  {
+    float* s_bias = reinterpret_cast<float*>(smem_gen + p.off_bias);
+    float* s_stats = reinterpret_cast<float*>(smem_gen + p.off_stats);
+    if (!glu) {
+      for (int i = threadIdx.x; i < p.cols_alloc; i += NUM_THREADS) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+    } else {  // [0,cols) = value-half bias, [cols, 2*cols) = gate-half bias
+      for (int i = threadIdx.x; i < p.cols_alloc; i += NUM_THREADS) {
+        s_bias[i] = (p.bias && i < p.D2) ? p.bias[i] : 0.f;
+        s_bias[p.cols_alloc + i] = (p.bias && i < p.D2) ? p.bias[p.D2 + i] : 0.f;
+      }
+    }
+    if (p.stats)
+      for (int i = threadIdx.x; i < 2 * p.cols_alloc; i += NUM_THREADS) s_stats[i] = 0.f;
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   tc_fence_before();
@@ -160,8 +190,6 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   const int k_iters = p.taps * p.k_blocks;
-  const int half_n = p.block_n >> 1;
-  const bool glu = p.act == SD_ACT_GLU;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -180,12 +208,12 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int shift = (j - (p.taps - 1) / 2) * p.dil;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(empty_bar(s), ph ^ 1);
-            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+            const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + A_BYTES;
             mbar_arrive_expect_tx(full_bar(s), stage_tx);
             tma_load_3d(sa, &tmap_a, full_bar(s), kb * BLOCK_K, t0 + shift, b);
             tma_load_3d(sb, &tmap_w, full_bar(s), kb * BLOCK_K, row0, g * p.taps + j);
             tma_load_3d(sb + half_n * (BLOCK_K * 2), &tmap_w, full_bar(s), kb * BLOCK_K, row1, g * p.taps + j);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -207,7 +235,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024);
@@ -215,16 +243,29 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0);
           }
           umma_commit(empty_bar(s));
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         umma_commit(tfull_bar(acc));
       }
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int hsel = ew >> 2;   // which half of the tile's column chunks this warp owns
     const int row = quad * 32 + lane;
+    const uint32_t s_bias = smem_base + p.off_bias;
+    float* s_stats = reinterpret_cast<float*>(smem_gen + p.off_stats);
+    const uint32_t stg0 = smem_base + p.off_stg0 + row * p.pitch;
+    const uint32_t stg1 = smem_base + p.off_stg1 + row * p.pitch;
+    // chunk range [ch0, ch1) of 16-column chunks owned by this thread
+    const int nch = glu ? (half_n >> 4) : (p.block_n >> 4);
+    const int ch0 = hsel ? (nch + 1) / 2 : 0;
+    const int ch1 = hsel ? nch : (nch + 1) / 2;
+    const int seg_col = ch0 * 16, seg_cols = (ch1 - ch0) * 16;
+    uint32_t res_ph = 0;
+
     int it_tile = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
       const int acc = it_tile & 1;
@@ -234,44 +275,62 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int t = (m_idx % p.m_tiles_per_sample) * BLOCK_M + row;
       const bool valid = t < p.T;
       const size_t grow = (size_t)b * p.T + (valid ? t : 0);
+      const int n0 = glu ? n_idx * half_n : n_idx * p.block_n;  // first output channel of the tile
+      const int lim = glu ? p.Op : p.Np;
+      // number of this thread's columns that exist in global memory (multiple of 8)
+      int gcols = lim - (n0 + seg_col);
+      gcols = gcols < 0 ? 0 : (gcols > seg_cols ? seg_cols : gcols);
+
+      // previous tile's bulk stores must have finished reading this thread's staging lines
+      bulk_wait_read0();
+      if (p.res) {
+        const uint32_t bytes = (valid && gcols > 0) ? (uint32_t)gcols * 2 : 0;
+        if (bytes) {
+          mbar_arrive_expect_tx(res_bar(ew), bytes);
+          bulk_load(stg0 + seg_col * 2, p.res + grow * p.Np + n0 + seg_col, bytes, res_bar(ew));
+        } else {
+          mbar_arrive(res_bar(ew));
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
+      if (p.res) {
+        mbar_wait(res_bar(ew), res_ph);
+        res_ph ^= 1;
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * MAX_BLOCK_N;
       float sumsq = 0.f;
 
       if (!glu) {
-        const int n0 = n_idx * p.block_n;
-        for (int cc = 0; cc < p.block_n; cc += 16) {
-          const int nb = n0 + cc;
-          if (nb >= p.Np) break;
+        for (int c = ch0; c < ch1; ++c) {
+          const int cc = c * 16, nb = n0 + cc;
           uint32_t r[16];
           tmem_ld16(taddr + cc, r);
           tmem_ld_wait();
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = __uint_as_float(r[i]);
-            if (p.bias && nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
-          }
-          if (p.res && valid) load16_bf16_add(p.res + grow * p.Np + nb, v, nb, p.Np);
-          if (p.preact && valid) store16_bf16(p.preact + grow * p.Np + nb, v, nb, p.Np);
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          lds16_f32_add(s_bias + nb * 4, v);
+          if (p.res && valid && nb < p.Np) lds16_bf16_add(stg0 + cc * 2, v);
           if (p.act == SD_ACT_GELU) {
+            if (p.preact) sts16_bf16(stg0 + cc * 2, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
+            if (p.out_mode == SD_OUT_BTC) sts16_bf16(stg1 + cc * 2, v);
+          } else {
+            sts16_bf16(stg0 + cc * 2, v);
           }
-          if (p.out_mode == SD_OUT_BTC) {
-            if (valid) store16_bf16(p.out_btc + grow * p.Np + nb, v, nb, p.Np);
-          } else if (valid) {
+          if (p.out_mode == SD_OUT_NCT_F32 && valid) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (nb + i < p.N) p.out_nct[((size_t)b * p.N + nb + i) * p.T + t] = v[i];
-          }
-          if (p.rownorm2 && valid) {
+            if (p.rownorm2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.N) sumsq += v[i] * v[i];
+              for (int i = 0; i < 16; ++i)
+                if (nb + i < p.N) sumsq += v[i] * v[i];
+            }
           }
-          if (p.stats) {  // statistics of the values as stored (bf16-rounded), invalid rows contribute 0
+          if (p.stats) {  // statistics of the values as stored (bf16-rounded); invalid rows contribute 0
             float s1[16], s2[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -281,19 +340,29 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
             float cs = warp_colsum16(s1, lane);
             float cq = warp_colsum16(s2, lane);
-            const int n = nb + col_of_lane(lane);
-            if ((lane & 1) == 0 && n < p.Np) {
-              atomicAdd(p.stats + n, (double)cs);
-              atomicAdd(p.stats + p.Np + n, (double)cq);
+            if ((lane & 1) == 0) {
+              const int n = nb + col_of_lane(lane);
+              atomicAdd(s_stats + n, cs);
+              atomicAdd(s_stats + p.cols_alloc + n, cq);
             }
           }
         }
+        if (valid && gcols > 0) {
+          fence_proxy_async();
+          const uint32_t bytes = (uint32_t)gcols * 2;
+          const size_t goff = grow * p.Np + n0 + seg_col;
+          if (p.act == SD_ACT_GELU) {
+            if (p.preact) bulk_store(p.preact + goff, stg0 + seg_col * 2, bytes);
+            if (p.out_mode == SD_OUT_BTC) bulk_store(p.out_btc + goff, stg1 + seg_col * 2, bytes);
+          } else {
+            bulk_store(p.out_btc + goff, stg0 + seg_col * 2, bytes);
+          }
+        }
+        bulk_commit();
       } else {
-        // GLU: tile columns [0,half) = a channels c0.., [half, 2*half) = gate channels D2+c0..
-        const int c0 = n_idx * half_n;
-        for (int cc = 0; cc < half_n; cc += 16) {
-          const int cb = c0 + cc;
-          if (cb >= p.Op) break;
+        // GLU: tile columns [0,half) = value channels n0.., [half, 2*half) = gate channels D2+n0..
+        for (int c = ch0; c < ch1; ++c) {
+          const int cc = c * 16, cb = n0 + cc;
           uint32_t ra[16], rb[16];
           tmem_ld16(taddr + cc, ra);
           tmem_ld16(taddr + half_n + cc, rb);
@@ -303,21 +372,32 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int i = 0; i < 16; ++i) {
             va[i] = __uint_as_float(ra[i]);
             vb[i] = __uint_as_float(rb[i]);
-            if (p.bias && cb + i < p.D2) {
-              va[i] += __ldg(p.bias + cb + i);
-              vb[i] += __ldg(p.bias + p.D2 + cb + i);
-            }
           }
-          if (valid) {
-            if (p.preact) {
-              store16_bf16(p.preact + grow * p.Np + cb, va, cb, p.D2);
-              store16_bf16(p.preact + grow * p.Np + p.D2 + cb, vb, cb, p.D2);
-            }
+          lds16_f32_add(s_bias + cb * 4, va);
+          lds16_f32_add(s_bias + (p.cols_alloc + cb) * 4, vb);
+          if (p.preact) {
+            sts16_bf16(stg0 + cc * 2, va);
+            sts16_bf16(stg0 + (half_n + cc) * 2, vb);
+          }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) va[i] = (cb + i < p.D2) ? va[i] * sigmoid_f(vb[i]) : 0.f;
-            store16_bf16(p.out_btc + grow * p.Op + cb, va, cb, p.Op);
-          }
+          for (int i = 0; i < 16; ++i) va[i] = (cb + i < p.D2) ? va[i] * sigmoid_f(vb[i]) : 0.f;
+          sts16_bf16(stg1 + cc * 2, va);
         }
+        if (valid && gcols > 0) {
+          fence_proxy_async();
+          const uint32_t bytes = (uint32_t)gcols * 2;
+          if (p.preact) {
+            // D2 % 8 == 0 on this path, so the pre-activation segments never run past their half
+            int pc = p.D2 - (n0 + seg_col);
+            pc = pc < 0 ? 0 : (pc > seg_cols ? seg_cols : pc);
+            if (pc > 0) {
+              bulk_store(p.preact + grow * p.Np + n0 + seg_col, stg0 + seg_col * 2, (uint32_t)pc * 2);
+              bulk_store(p.preact + grow * p.Np + p.D2 + n0 + seg_col, stg0 + (half_n + seg_col) * 2, (uint32_t)pc * 2);
+            }
+          }
+          bulk_store(p.out_btc + grow * p.Op + n0 + seg_col, stg1 + seg_col * 2, bytes);
+        }
+        bulk_commit();
       }
       if (p.rownorm2) {
         sumsq = warp_sum(sumsq);
@@ -327,6 +407,18 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
+    bulk_wait0();
+    if (p.stats) {
+      epi_bar_sync();
+      const int et = threadIdx.x - 64;
+      for (int i = et; i < p.n_tiles * p.block_n && i < p.Np; i += NUM_EPI_WARPS * 32) {
+        float a = s_stats[i], q = s_stats[p.cols_alloc + i];
+        if (a != 0.f || q != 0.f) {
+          atomicAdd(p.stats + i, (double)a);
+          atomicAdd(p.stats + p.Np + i, (double)q);
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -334,12 +426,12 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// pick the N tile: multiple of 16, <= 256, minimal padded total, fewest tiles on ties
-int pick_block_n(int n_total) {
-  int best_bn = 16, best_pad = 1 << 30;
+// pick the N tile: multiple of `gran`, <= 256, minimal padded total, fewest tiles on ties
+int pick_block_n(int n_total, int gran) {
+  int best_bn = gran, best_pad = 1 << 30;
   const int min_tiles = (n_total + MAX_BLOCK_N - 1) / MAX_BLOCK_N;
   for (int nt = min_tiles; nt <= min_tiles + 3; ++nt) {
-    int bn = ((n_total + nt - 1) / nt + 15) / 16 * 16;
+    int bn = ((n_total + nt - 1) / nt + gran - 1) / gran * gran;
     if (bn > MAX_BLOCK_N) continue;
     int pad = bn * nt;
     if (pad < best_pad) { best_pad = pad; best_bn = bn; }
@@ -397,13 +489,19 @@ bool conv_fwd_tc_supported(const sd_conv_args& a) {
   if (a.act == SD_ACT_GLU && ((a.N / 2) % 8 != 0 || a.out_mode != SD_OUT_BTC || a.N % 2)) return false;
   if (a.stats && (a.act != SD_ACT_NONE || a.out_mode != SD_OUT_BTC)) return false;
   if (a.rownorm2 && a.out_mode != SD_OUT_NCT_F32) return false;
-  if (((uintptr_t)a.in & 15) || ((uintptr_t)a.w & 15)) return false;
+  if (a.res && (a.act != SD_ACT_NONE || a.out_mode != SD_OUT_BTC)) return false;
+  if (a.out_mode == SD_OUT_NCT_F32 && a.act != SD_ACT_GELU) return false;
+  if (((uintptr_t)a.in & 15) || ((uintptr_t)a.w & 15) || ((uintptr_t)a.out & 15) || ((uintptr_t)a.res & 15) ||
+      ((uintptr_t)a.preact & 15))
+    return false;
+  if (a.Np > 4096) return false;
   return true;
 }
 
 int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   const bool glu = a.act == SD_ACT_GLU;
   FwdParams p;
+  memset(&p, 0, sizeof(p));
   p.bias = a.bias;
   p.res = reinterpret_cast<const __nv_bfloat16*>(a.res);
   p.out_btc = reinterpret_cast<__nv_bfloat16*>(a.out);
@@ -417,18 +515,37 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   p.D2 = glu ? a.N / 2 : 0;
   p.Op = glu ? (p.D2 + 7) / 8 * 8 : 0;
   if (glu) {
-    const int half = pick_block_n(2 * p.Op) / 2;   // output channels per tile
-    p.block_n = 2 * ((half + 7) / 8 * 8);
-    if (p.block_n % 16) p.block_n += 8;            // keep UMMA_N a multiple of 16 (half stays a multiple of 8)
-    if (p.block_n > MAX_BLOCK_N) p.block_n = MAX_BLOCK_N;
+    p.block_n = pick_block_n(2 * p.Op, 32);   // value half and gate half: each a multiple of 16 columns
     p.n_tiles = (p.Op + p.block_n / 2 - 1) / (p.block_n / 2);
+    p.cols_alloc = p.n_tiles * (p.block_n / 2);
   } else {
-    p.block_n = pick_block_n(a.Np);
+    p.block_n = pick_block_n(a.Np, 16);
     p.n_tiles = (a.Np + p.block_n - 1) / p.block_n;
+    p.cols_alloc = p.n_tiles * p.block_n;
   }
   p.m_tiles_per_sample = (a.T + BLOCK_M - 1) / BLOCK_M;
   p.num_tiles = a.B * p.m_tiles_per_sample * p.n_tiles;
   p.k_blocks = (a.Kp + BLOCK_K - 1) / BLOCK_K;
+
+  // shared-memory plan
+  p.stage_bytes = A_BYTES + p.block_n * BLOCK_K * 2;
+  p.pitch = p.block_n * 2 + 16;
+  const bool need_stg1 = glu || (a.act == SD_ACT_GELU && a.out_mode == SD_OUT_BTC);
+  const int stg_bytes = BLOCK_M * p.pitch;
+  const int tail = stg_bytes * (need_stg1 ? 2 : 1) + (glu ? 2 : 1) * p.cols_alloc * 4 + 2 * p.cols_alloc * 4 + 512;
+  int stages = (SMEM_LIMIT - 1024 - tail) / p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  SD_REQUIRE(stages >= 2, "conv_fwd_tc: not enough shared memory for block_n=%d", p.block_n);
+  p.stages = stages;
+  int off = stages * p.stage_bytes;
+  p.off_stg0 = off; off += stg_bytes;
+  p.off_stg1 = off; if (need_stg1) off += stg_bytes;
+  p.off_bias = off; off += (glu ? 2 : 1) * p.cols_alloc * 4;
+  p.off_stats = off; off += 2 * p.cols_alloc * 4;
+  off = (off + 15) / 16 * 16;
+  p.off_bar = off; off += 512;
+  const int smem_bytes = off + 1024;
+  SD_REQUIRE(smem_bytes <= SMEM_LIMIT, "conv_fwd_tc: shared-memory plan %d exceeds limit", smem_bytes);
 
   CUtensorMap ta, tw;
   if (make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, (uint64_t)a.Kp, (uint64_t)a.T, (uint64_t)a.B,
@@ -440,11 +557,11 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    SD_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SD_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_fwd_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tw, p);
+  conv_fwd_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(ta, tw, p);
   return check_launch("conv_fwd_tc");
 }
 
