@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the BrainEncoder + CLIPLoss training hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1]/[2] -- synthetic Gwilliams2022-shape MEG
+(208 sensors, 360 samples, 27 subjects, D1=270, D2=320, F=1024), B=256 per GPU, random-init weights.
+A step is  Z = encoder(X, ids); loss = clip(Y, Z); loss.backward()  (+ gradient all-reduce for N>1).
+
+Prints ONE JSON line (rank 0).  See the repo-level prompt/DESIGN.md for the key meanings:
+value = samples/s with inputs resident in HBM; e2e = same through the public API from pinned host
+buffers incl. H2D copies, Adam step and the loss read-back; roofline = the tcgen05 conv kernel
+(forward + data-gradient launches) against the measured bf16 peak; cpu_baseline = the oracle
+(oracle/restate.py, the CPU restatement of the reference) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "speech-decoding_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+CFG = dict(C=208, T=360, S=27, D1=270, D2=320, F=1024, K=32, B=256)
+# forward FLOPs per sample (2*MAC), SURVEY.md §8(d) / BASELINE.md §3
+ENC_FWD_GF, ENC_BWD_GF = 5.154, 10.267
+
+
+def step_gflop_per_sample(global_b):
+    clip = 2.0 * global_b * CFG["F"] * CFG["T"] / 1e9
+    return ENC_FWD_GF + ENC_BWD_GF + 2 * clip
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return dict(tflops_burst=d.get("bf16_tflops", 1590.0), tflops=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm_gbs=d.get("hbm_gbs", 6650.0), source="measured")
+    return dict(tflops_burst=1590.0, tflops=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = []
+        reasons = set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); out["sm_max_mhz"] = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]           # upper half = samples under load
+            out["sm_mhz"] = float(np.median(busy))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def make_args_ns():
+    from oracle.restate import make_args
+    return make_args(D1=CFG["D1"], D2=CFG["D2"], F_=CFG["F"], K=CFG["K"], num_subjects=CFG["S"],
+                     num_channels=CFG["C"], last4layers=True)
+
+
+def synth(B, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(B, CFG["C"], CFG["T"], generator=g).clamp_(-20, 20)
+    Y = torch.randn(B, CFG["F"], CFG["T"], generator=g)
+    ids = torch.randint(0, CFG["S"], (B,), generator=g, dtype=torch.int32)
+    if pin:
+        X, Y = X.pin_memory(), Y.pin_memory()
+    return X, Y, ids
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(steps, warmup, sample_b=64):
+    from oracle import restate
+    torch.set_num_threads(os.cpu_count() or 1)
+    args = make_args_ns()
+    sd, loc = restate.init_state_dict(args, CFG["C"])
+    X, Y, ids = synth(sample_b, 123)
+    temp = torch.tensor([5.1])
+    mask = restate.dropout_mask(loc, args.d_drop, 7)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        restate.train_step(sd, X, Y, ids.tolist(), temp, mask)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    return dict(value=sample_b / (ms / 1e3), ms_per_step=ms, cores=torch.get_num_threads(), kind="port",
+                sample="oracle/restate.py fwd+bwd, fp32, B=%d of the cfg2 shapes, %d timed steps (samples/s is batch-size "
+                       "independent to first order on CPU)" % (sample_b, steps))
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    r = cpu_oracle_rate(max(1, min(a.steps, 3)), max(1, min(a.warmup, 1)))
+    line = {"impl": "reference", "metric": "BrainEncoder+CLIP train samples/sec", "value": round(r["value"], 2),
+            "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(r["ms_per_step"], 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "cfg2 Gwilliams2022-shape (208 sensors x 360 samples, 27 subjects, D1=270 D2=320 F=1024); "
+                                   "reference CPU path = oracle port, bounded sample B=64"},
+            "cpu_baseline": {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": round(r["value"], 2), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a, rank, world, local_rank):
+    import torch.distributed as dist
+    import sd_b200
+    from sd_b200 import _native as nat, ops
+    from speech_decoding.models import BrainEncoder
+    from speech_decoding.utils.loss import CLIPLoss
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    sd_b200.set_precision(a.precision)
+    torch.manual_seed(0)           # identical replicas on every rank
+    np.random.seed(0)              # identical dropout centres on every rank
+    args = make_args_ns()
+    enc = BrainEncoder(args).to(dev).train()
+    crit = CLIPLoss(args).to(dev).train()
+    opt = torch.optim.Adam(list(enc.parameters()) + list(crit.parameters()), lr=3e-4)
+    if world > 1:
+        from sd_b200.dist import DataParallel
+        DataParallel(enc, crit, sync_bn=bool(a.sync_bn))
+    B = a.batch
+    Xh, Yh, ids = synth(B, 1000 + rank, pin=True)
+    X, Y = Xh.to(dev), Yh.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def hot_step():
+        Z = enc(X, ids)
+        loss = crit(Y, Z)
+        for p in opt.param_groups[0]["params"]:
+            p.grad = None
+        loss.backward()
+        return loss
+
+    # counting launches through the C ABI
+    counter = {"n": 0}
+    orig_call = nat.call
+
+    def counting_call(name, *args_):
+        counter["n"] += 1
+        return orig_call(name, *args_)
+
+    for _ in range(a.warmup):
+        hot_step()
+    barrier()
+    nat.call = counting_call
+    ops.nat.call = counting_call
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = hot_step()
+    e1.record()
+    barrier()
+    launches = counter["n"]
+    nat.call = orig_call
+    ops.nat.call = orig_call
+    ms = e0.elapsed_time(e1) / a.steps
+    clk = clocks.stop() if clocks else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    value = world * B / (ms / 1e3)
+    loss_val = float(loss)
+
+    # ---- roofline of the dominant kernel (tcgen05 conv fwd/dgrad), CUDA events around each launch ----
+    roof = None
+    if a.precision == "bf16":
+        recs = []
+        orig_conv = ops.conv_fwd
+
+        def timed_conv(inp, w, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig_conv(inp, w, **kw)
+            e.record()
+            Bn, Tn, _ = inp.shape
+            recs.append((s, e, 2.0 * Bn * Tn * kw["K"] * kw["N"] * kw.get("taps", 1)))
+            return r
+
+        ops.conv_fwd = timed_conv
+        import sd_b200.engine as eng
+        eng.ops.conv_fwd = timed_conv
+        nprof = min(a.steps, 5)
+        for _ in range(nprof):
+            hot_step()
+        torch.cuda.synchronize()
+        ops.conv_fwd = orig_conv
+        eng.ops.conv_fwd = orig_conv
+        tot_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+        tot_fl = sum(f for _, _, f in recs)
+        peaks = measured_peaks()
+        ach = tot_fl / (tot_ms / 1e3) / 1e12
+        roof = {"kernel": "conv_fwd_tc_kernel (implicit-GEMM conv forward + data-gradient, %d launches/step)" % (len(recs) // nprof),
+                "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["tflops"], 4), "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                "avg_launch_ms": round(tot_ms / len(recs), 4), "share_of_step": round(tot_ms / nprof / ms, 3),
+                "traffic": None}
+
+    # ---- end to end: pinned host inputs, H2D every step (prefetched on a copy stream), Adam, loss read-back ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(X), torch.empty_like(Y)) for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i][0].copy_(Xh, non_blocking=True)
+            bufs[i][1].copy_(Yh, non_blocking=True)
+            evs[i].record(copy_stream)
+
+    def e2e_loop(n):
+        prefetch(0)
+        last = None
+        for i in range(n):
+            cur = i & 1
+            if i + 1 < n:
+                prefetch(cur ^ 1)
+            torch.cuda.current_stream().wait_event(evs[cur])
+            Xd, Yd = bufs[cur]
+            Z = enc(Xd, ids)
+            loss = crit(Yd, Z)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            last = loss.item()                 # D2H read of the step's result (train.py:196)
+        return last
+
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(a.steps)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+    e2e_value = world * B / (e2e_ms / 1e3)
+
+    if rank != 0:
+        return
+    gflop = step_gflop_per_sample(world * B)
+    line = {"metric": "BrainEncoder+CLIP train samples/sec", "value": round(value, 1), "unit": "samples/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+            "config": {"workload": "cfg2/cfg3 Gwilliams2022-shape MEG: B=%d per GPU, 208 sensors x 360 samples, 27 subjects, "
+                                   "D1=270 D2=320 F=1024 K=32; step = encoder fwd + CLIP loss + backward%s"
+                                   % (B, " + grad all-reduce, global-batch CLIP negatives" if world > 1 else ""),
+                       "global_batch": world * B, "precision": a.precision + (" activations, fp32 master weights/accumulate" if a.precision == "bf16" else ""),
+                       "l2": "working set (>2 GB of activations, 454 MB of inputs) exceeds the 126 MB L2",
+                       "sync_bn": bool(a.sync_bn) if world > 1 else None, "loss": round(loss_val, 4)},
+            "model_tflops_per_s": round(value * gflop / 1e3, 1),
+            "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 3),
+                    "h2d_bytes_per_step": int(Xh.numel() * 4 + Yh.numel() * 4), "d2h_bytes_per_step": 4,
+                    "includes": "H2D of X,Y from pinned memory (double-buffered), fwd, loss, backward, Adam step, loss.item()"},
+            "gpu_launches": launches, "clocks": clk}
+    if roof:
+        line["roofline"] = roof
+    if world == 1 and not a.no_cpu:
+        r = cpu_oracle_rate(2, 1)
+        line["cpu_baseline"] = {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                                "sample": r["sample"]}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=CFG["B"])
+    ap.add_argument("--sync-bn", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(a, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

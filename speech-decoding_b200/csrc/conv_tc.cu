@@ -565,10 +565,4 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   return check_launch("conv_fwd_tc");
 }
 
-bool conv_wgrad_tc_supported(const sd_wgrad_args&) { return false; }
-int conv_wgrad_tc(const sd_wgrad_args&, cudaStream_t) {
-  set_error("tcgen05 wgrad not built");
-  return 1;
-}
-
 }  // namespace sd

@@ -1,0 +1,248 @@
+// tcgen05 / TMEM / TMA Conv1d weight gradient (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   dw[g, n, c, j] += sum_{b in group g} sum_t dy[b,t,n] * x[b, t + (j-(taps-1)/2)*dil, c]
+//   dbias[n]       += sum_{b,t} dy[b,t,n]
+// (autograd of nn.Conv1d, speech_decoding/models.py:97-109,128-150,188-189; the grouped form is the
+//  per-subject layer models.py:98-116 with samples bucketed by subject id.)
+//
+// GEMM view per CTA: D[128 out-channels n, BLOCK_C in-channels c] for ONE tap j, contracted over the
+// (sample, time) axis of a slice of the batch.  Both operands are read straight from the
+// channels-last activations: the contraction index t is the row index, so A = dy^T and B = x^T are
+// "MN-major" UMMA operands (64 contiguous channels = one 128-byte swizzle row per time step); the
+// tap shift is a TMA row coordinate and rows outside [0,T) are zero-filled (= "same" padding).
+// Split-K over the batch: work item = (n-tile, c-tile, tap, group, split); one item per CTA; the fp32
+// tile is added to dw (PyTorch (N,K,taps) layout, via element strides) with red.global.add.f32.
+// dbias comes from one extra N=16 MMA per k-step against a constant tile of ones.
+#include "tc_common.cuh"
+
+namespace sd {
+
+using namespace tc;
+
+namespace {
+
+constexpr int BLOCK_MN = 128;     // out-channel tile (UMMA M)
+constexpr int BLOCK_T = 64;       // contraction block: 64 time steps
+constexpr int ATOM_BYTES = 64 * 128;  // 64 time rows x 128 B (64 channels)
+constexpr int MAX_C_ATOMS = 4;    // BLOCK_C <= 256
+constexpr int STAGES = 4;
+constexpr int TMEM_COLS = 512;
+constexpr int BIAS_COL = 256;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int ONES_BYTES = 2048;
+
+struct WgParams {
+  float* dw;
+  float* dbias;
+  const int* sample_order;
+  const int* group_offsets;
+  int B, T, N, K, taps, dil, G;
+  long long gs, sn, sk, sj;
+  int block_c, c_atoms, n_tiles, c_tiles, nsplit, stage_bytes;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                     const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t ones_base = smem_base + STAGES * p.stage_bytes;
+  const uint32_t bar_base = ones_base + ONES_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- decode the work item ----
+  int item = blockIdx.x;
+  const int split = item % p.nsplit; item /= p.nsplit;
+  const int g = item % p.G; item /= p.G;
+  const int j = item % p.taps; item /= p.taps;
+  const int c_tile = item % p.c_tiles;
+  const int n_tile = item / p.c_tiles;
+  const int n0 = n_tile * BLOCK_MN, c0 = c_tile * p.block_c;
+  const int pos0 = p.group_offsets ? p.group_offsets[g] : 0;
+  const int pos1 = p.group_offsets ? p.group_offsets[g + 1] : p.B;
+  const int cnt = pos1 - pos0;
+  const int per = (cnt + p.nsplit - 1) / p.nsplit;
+  const int s_begin = pos0 + split * per;
+  const int s_end = min(pos1, s_begin + per);
+  if (s_begin >= s_end) return;  // uniform for the whole CTA: nothing allocated yet
+  const bool do_bias = p.dbias != nullptr && j == 0 && c_tile == 0;
+  const int t_blocks = (p.T + BLOCK_T - 1) / BLOCK_T;
+  const int shift = (j - (p.taps - 1) / 2) * p.dil;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_dy);
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  {  // constant tile of bf16 ones for the bias MMA
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + STAGES * p.stage_bytes);
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NUM_THREADS) ones[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t stage_tx = (uint32_t)(2 + p.c_atoms) * ATOM_BYTES;
+      for (int pos = s_begin; pos < s_end; ++pos) {
+        const int b = p.sample_order ? __ldg(p.sample_order + pos) : pos;
+        for (int tb = 0; tb < t_blocks; ++tb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + 2 * ATOM_BYTES;
+          mbar_arrive_expect_tx(full_bar(s), stage_tx);
+          tma_load_3d(sa, &tmap_dy, full_bar(s), n0, tb * BLOCK_T, b);
+          tma_load_3d(sa + ATOM_BYTES, &tmap_dy, full_bar(s), n0 + 64, tb * BLOCK_T, b);
+          for (int a = 0; a < p.c_atoms; ++a)
+            tma_load_3d(sb + a * ATOM_BYTES, &tmap_x, full_bar(s), c0 + 64 * a, tb * BLOCK_T + shift, b);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(/*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1, BLOCK_MN, (uint32_t)p.block_c);
+      const uint32_t idesc_b = make_idesc(1, 1, 1, BLOCK_MN, 16);
+      int s = 0;
+      uint32_t ph = 0;
+      const int iters = (s_end - s_begin) * t_blocks;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + 2 * ATOM_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_T / 16; ++k) {
+          // 16 time rows = 2048 B inside each 64-channel atom; atoms are ATOM_BYTES apart (LBO);
+          // consecutive 8-row groups are 1024 B apart (SBO)
+          const uint64_t ad = make_smem_desc(sa + k * 2048, ATOM_BYTES, 1024);
+          const uint64_t bd = make_smem_desc(sb + k * 2048, ATOM_BYTES, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0);
+          if (do_bias) {
+            const uint64_t od = make_smem_desc(ones_base, ATOM_BYTES, 1024);
+            umma_f16(tmem_base + BIAS_COL, ad, od, idesc_b, (it | k) != 0);
+          }
+        }
+        umma_commit(empty_bar(s));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: fp32 tile -> red.add into dw =====================
+    const int ew = warp - 2, quad = warp & 3, hsel = ew >> 2;
+    const int n = n0 + quad * 32 + lane;
+    const int nch = p.block_c >> 4;
+    const int ch0 = hsel ? (nch + 1) / 2 : 0, ch1 = hsel ? nch : (nch + 1) / 2;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* dwn = p.dw + (long long)g * p.gs + (long long)n * p.sn + (long long)j * p.sj;
+    for (int c = ch0; c < ch1; ++c) {
+      uint32_t r[16];
+      tmem_ld16(taddr + c * 16, r);
+      tmem_ld_wait();
+      if (n < p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int cc = c0 + c * 16 + i;
+          if (cc < p.K) atomicAdd(dwn + (long long)cc * p.sk, __uint_as_float(r[i]));
+        }
+      }
+    }
+    if (do_bias && hsel == 0) {
+      uint32_t r[16];
+      tmem_ld16(taddr + BIAS_COL, r);
+      tmem_ld_wait();
+      if (n < p.N) atomicAdd(p.dbias + n, __uint_as_float(r[0]));
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int pick_block_c(int kp) {
+  // multiple of 16, <= 256, minimal padding, fewest tiles on ties
+  int best = 16, best_pad = 1 << 30;
+  const int min_tiles = (kp + 255) / 256;
+  for (int nt = min_tiles; nt <= min_tiles + 3; ++nt) {
+    int bc = ((kp + nt - 1) / nt + 15) / 16 * 16;
+    if (bc > 256) continue;
+    if (bc * nt < best_pad) { best_pad = bc * nt; best = bc; }
+  }
+  return best;
+}
+
+}  // namespace
+
+bool conv_wgrad_tc_supported(const sd_wgrad_args& a) {
+  if (a.dtype != SD_BF16) return false;
+  if (((uintptr_t)a.dout & 15) || ((uintptr_t)a.in & 15)) return false;
+  if ((a.group_offsets == nullptr) != (a.G == 1)) return false;
+  return true;
+}
+
+int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.dw = a.dw; p.dbias = a.dbias; p.sample_order = a.sample_order; p.group_offsets = a.group_offsets;
+  p.B = a.B; p.T = a.T; p.N = a.N; p.K = a.K; p.taps = a.taps; p.dil = a.dil; p.G = a.G;
+  p.gs = a.gs; p.sn = a.sn; p.sk = a.sk; p.sj = a.sj;
+  p.block_c = pick_block_c(a.Kp);
+  p.c_atoms = (p.block_c + 63) / 64;
+  p.n_tiles = (a.Np + BLOCK_MN - 1) / BLOCK_MN;
+  p.c_tiles = (a.Kp + p.block_c - 1) / p.block_c;
+  const int base_items = p.n_tiles * p.c_tiles * a.taps * a.G;
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int nsplit = a.G > 1 ? 1 : sms / base_items;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > a.B) nsplit = a.B;
+  p.nsplit = nsplit;
+  p.stage_bytes = (2 + p.c_atoms) * ATOM_BYTES;
+  const int smem_bytes = STAGES * p.stage_bytes + ONES_BYTES + 256 + 1024;
+
+  CUtensorMap tdy, tx;
+  if (make_tmap_3d(&tdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.dout, (uint64_t)a.Np, (uint64_t)a.T, (uint64_t)a.B,
+                   (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, 64, BLOCK_T, 1))
+    return 1;
+  if (make_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, (uint64_t)a.Kp, (uint64_t)a.T, (uint64_t)a.B,
+                   (uint64_t)a.Kp * 2, (uint64_t)a.T * a.Kp * 2, 64, BLOCK_T, 1))
+    return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SD_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_wgrad_tc_kernel<<<base_items * nsplit, NUM_THREADS, smem_bytes, st>>>(tdy, tx, p);
+  return check_launch("conv_wgrad_tc");
+}
+
+}  // namespace sd

@@ -27,7 +27,33 @@ def build(cfg, precision):
     return args, BrainEncoder(args).to(DEV), CLIPLoss(args).to(DEV)
 
 
-def grad_check(enc, ref_grads, absent, tol):
+def err_fn(precision):
+    """fp32 mode: max-abs error over max-abs value (strict).  bf16 mode: normwise relative error
+    ||a-b||/||b|| -- every stored activation is rounded to 8 mantissa bits, so individual elements of a
+    17-layer network carry a few 1e-2 of noise while the tensors as a whole agree to <2e-2."""
+    return G.rel_err if precision == "fp32" else G.rel_l2
+
+
+def autocast_noise(sd, X, Y, ids, temp, mask, reduction="mean"):
+    """Error of PyTorch's own bf16 autocast of the oracle against the fp32 oracle, same inputs and
+    weights, on the GPU: the noise floor of the number format for this network.  Returns normwise
+    errors {"Z":..., "grads": {name: ...}}.  The bf16 mode must meet the north_star tolerance or, where
+    bf16 itself cannot, stay within 1.25x of this floor."""
+    dev = torch.device(DEV)
+    def run(autocast):
+        s2 = {k: v.clone().to(dev) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            return restate.train_step(s2, X.to(dev), Y.to(dev), ids, temp.to(dev), None if mask is None else mask.to(dev),
+                                      reduction=reduction)
+    a, b = run(True), run(False)
+    out = {"Z": G.rel_l2(a["Z"].float(), b["Z"]), "loss": G.rel_err(a["loss"].float(), b["loss"]), "grads": {}}
+    for k, g in b["grads"].items():
+        if g is not None and a["grads"][k] is not None:
+            out["grads"][k] = G.rel_l2(a["grads"][k], g)
+    return out
+
+
+def grad_check(enc, ref_grads, absent, tol, err=G.rel_err, floor_noise=None):
     worst = ("", 0.0)
     named = dict(enc.named_parameters())
     for k, gr in ref_grads.items():
@@ -35,23 +61,27 @@ def grad_check(enc, ref_grads, absent, tol):
             continue
         g = named[k].grad
         assert g is not None, "missing grad " + k
-        scale = float(gr.abs().max())
+        l2 = err is G.rel_l2
+        scale = float(gr.norm()) if l2 else float(gr.abs().max())
         if k.endswith("bias"):          # zero-by-construction biases: compare on the layer's weight-grad scale
             wk = k[:-4] + "weight"
             if wk in ref_grads and ref_grads[wk] is not None:
-                scale = max(scale, float(ref_grads[wk].abs().max()))
-        e = G.rel_err(g, gr, floor=scale)
+                w = ref_grads[wk]
+                scale = max(scale, float(w.norm()) / (w.numel() / gr.numel()) ** 0.5 if l2 else float(w.abs().max()))
+        e = err(g, gr, floor=scale)
         if e > worst[1]:
             worst = (k, e)
-        assert e < tol, "%s: rel err %.3e (tol %.1e)" % (k, e, tol)
+        t = tol if floor_noise is None else max(tol, 1.25 * floor_noise.get(k, 0.0))
+        assert e < t, "%s: rel err %.3e (tol %.1e)" % (k, e, t)
     for k in absent:
         assert named[k].grad is None, "grad should be None for absent subject: " + k
     return worst
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 2e-4), ("bf16", 2e-2, 6e-2)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 2e-4), ("bf16", 2e-2, 4e-2)])
 @pytest.mark.parametrize("name", G.names())
 def test_golden_train_step(name, precision, tol_out, tol_grad, monkeypatch):
+    E = err_fn(precision)
     g = G.load(name)
     args, enc, crit = build(g["cfg"], precision)
     enc.load_state_dict(g["sd0"])
@@ -59,18 +89,23 @@ def test_golden_train_step(name, precision, tol_out, tol_grad, monkeypatch):
         crit.temp.copy_(g["temp"].to(DEV))
     enc.train(); crit.train()
     monkeypatch.setattr(np.random, "randint", lambda *a, **k: int(g["drop_center"]))   # models.py:81 draw
+    noise = None
+    if precision == "bf16":
+        mask = restate.dropout_mask(g["loc"], float(g["cfg"]["d_drop"]), int(g["drop_center"]))
+        noise = autocast_noise(g["sd0"], g["X"], g["Y"], g["ids"].tolist(), g["temp"], mask, str(g["cfg"]["reduction"]))
+        tol_out = max(tol_out, 1.25 * noise["Z"])
     Z = enc(g["X"].to(DEV), g["ids"])
     assert Z.shape == g["Z"].shape and Z.dtype == torch.float32 and Z.is_contiguous()
     logits, loss = crit(g["Y"].to(DEV), Z, return_logits=True)
     loss.backward()
-    assert G.rel_err(Z, g["Z"]) < tol_out
-    assert G.rel_err(logits, g["logits"]) < tol_out * (1 if precision == "fp32" else 3)
+    assert E(Z, g["Z"]) < tol_out
+    assert E(logits, g["logits"]) < tol_out
     assert G.rel_err(loss, g["loss"]) < tol_out
     assert G.rel_err(crit.temp.grad, g["dtemp"]) < tol_grad
-    grad_check(enc, g["grad"], g["absent_grads"], tol_grad)
+    grad_check(enc, g["grad"], g["absent_grads"], tol_grad, E, None if noise is None else noise["grads"])
     sd1 = enc.state_dict()
     for k, v in g["sd1"].items():
-        assert G.rel_err(sd1[k].float(), v.float(), floor=1e-3) < tol_out, k
+        assert E(sd1[k].float(), v.float(), floor=1e-3) < tol_out, k
     # the other call forms
     with torch.no_grad():
         ls = crit(g["Y"].to(DEV), Z.detach(), fast=False)
@@ -92,7 +127,7 @@ def test_golden_eval_forward(name, precision, tol):
     with torch.no_grad():
         crit.temp.copy_(g["temp"].to(DEV))
         Ze = enc(g["X"].to(DEV), g["ids"])
-        assert G.rel_err(Ze, g["Z_eval"]) < tol
+        assert err_fn(precision)(Ze, g["Z_eval"]) < tol
         assert G.rel_err(crit(g["Y"].to(DEV), Ze), g["loss_eval"]) < tol
     # eval must not touch the running statistics
     for k, v in g["sd1"].items():
@@ -126,9 +161,15 @@ def run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad, center=3):
     loss.backward()
     mask = restate.dropout_mask(enc.subject_block.spatial_attention.spatial_dropout.loc, args.d_drop, center)
     ref = restate.train_step(sd, X, Y, ids.tolist(), crit.temp.detach().cpu(), mask)
-    assert G.rel_err(Z, ref["Z"]) < tol_out
+    E = err_fn(precision)
+    noise = None
+    if precision == "bf16":
+        noise = autocast_noise(sd, X, Y, ids.tolist(), crit.temp.detach().cpu(), mask)
+        tol_out = max(tol_out, 1.25 * noise["Z"])
+    assert E(Z, ref["Z"]) < tol_out
     assert G.rel_err(loss, ref["loss"]) < tol_out
-    worst = grad_check(enc, ref["grads"], [k for k, v in ref["grads"].items() if v is None], tol_grad)
+    worst = grad_check(enc, ref["grads"], [k for k, v in ref["grads"].items() if v is None], tol_grad, E,
+                       None if noise is None else noise["grads"])
     # top-10 retrieval indices identical excluding ties (north_star)
     _, _, ref_idx, ref_sim = restate.classifier(ref["Z"], Y)
     mine = restate.classifier(Z.detach().cpu(), Y)[2]
@@ -140,7 +181,7 @@ def run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad, center=3):
     return worst
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 3e-4), ("bf16", 2e-2, 6e-2)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 3e-4), ("bf16", 2e-2, 4e-2)])
 def test_cfg1_brennan_shape_vs_oracle(precision, tol_out, tol_grad):
     """BASELINE.json configs[0]: Brennan2018-shape EEG (60 ch, 3 s, B=64), full-width model."""
     args, X, Y, ids = oracle_case(B=64, C=60, T=360, S=33, D1=270, D2=320, Fo=1024, K=32, seed=1)
