@@ -175,9 +175,10 @@ int sd_clip_phase1(const float* dots, const float* xn2, const float* zn2, const 
 int sd_clip_phase2(const float* logits, const float* row_lse, const float* col_lse, const float* xn2,
                    const float* zn2, const float* temp, float scale, int diag0, float* coef, float* cz,
                    float* partial, int M, int N, void* stream);
-/* dz[j,d] = sum_i coef[i,j] * x[i,d] - cz[j] * z[j,d]   (appendix A.5) */
-int sd_clip_dz(const float* coef, const float* cz, const float* x, const float* z, float* dz, int M, int N,
-               int64_t D, void* stream);
+/* dz[j,d] = gscale * (sum_i coef[i,j] * x[i,d] - cz[j] * z[j,d])   (appendix A.5);
+ * gscale: device pointer to the upstream gradient of the scalar loss, or NULL (= 1) */
+int sd_clip_dz(const float* coef, const float* cz, const float* x, const float* z, float* dz, const float* gscale,
+               int M, int N, int64_t D, void* stream);
 
 #ifdef __cplusplus
 }

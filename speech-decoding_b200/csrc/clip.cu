@@ -193,7 +193,8 @@ clip_grad_kernel(const float* __restrict__ logits, const float* __restrict__ row
 // ---- dz[j,d] = sum_i coef[i,j] x[i,d] - cz[j] z[j,d] ----------------------------------------------
 __global__ void __launch_bounds__(256)
 clip_dz_kernel(const float* __restrict__ coef, const float* __restrict__ cz, const float* __restrict__ x,
-               const float* __restrict__ z, float* __restrict__ dz, int M, int N, int64_t D) {
+               const float* __restrict__ z, float* __restrict__ dz, const float* __restrict__ gscale, int M, int N,
+               int64_t D) {
   __shared__ float As[CK][CB + 4];  // coef[i][j]
   __shared__ float Bs[CK][CB + 4];  // x[i][d]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -234,10 +235,11 @@ clip_dz_kernel(const float* __restrict__ coef, const float* __restrict__ cz, con
     const int j = j0 + ty * 4 + a;
     if (j >= N) continue;
     const float c = cz[j];
+    const float gs = gscale ? gscale[0] : 1.f;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int64_t d = d0 + tx * 4 + b;
-      if (d < D) dz[(size_t)j * D + d] = acc[a][b] - c * z[(size_t)j * D + d];
+      if (d < D) dz[(size_t)j * D + d] = gs * (acc[a][b] - c * z[(size_t)j * D + d]);
     }
   }
 }
@@ -280,9 +282,9 @@ int sd_clip_phase2(const float* logits, const float* row_lse, const float* col_l
   return check_launch("clip_grad");
 }
 
-int sd_clip_dz(const float* coef, const float* cz, const float* x, const float* z, float* dz, int M, int N,
-               int64_t D, void* stream) {
-  clip_dz_kernel<<<dim3(cdiv(D, CB), cdiv(N, CB)), 256, 0, (cudaStream_t)stream>>>(coef, cz, x, z, dz, M, N, D);
+int sd_clip_dz(const float* coef, const float* cz, const float* x, const float* z, float* dz, const float* gscale,
+               int M, int N, int64_t D, void* stream) {
+  clip_dz_kernel<<<dim3(cdiv(D, CB), cdiv(N, CB)), 256, 0, (cudaStream_t)stream>>>(coef, cz, x, z, dz, gscale, M, N, D);
   return check_launch("clip_dz");
 }
 

@@ -116,60 +116,102 @@ __global__ void pack_weight_single_kernel(sd_pack_entry e) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// column statistics over (rows, Cp): each thread owns 4 adjacent channels, 8 row-lanes per block
+// 8-channel vectors (16 B of bf16 / 32 B of fp32).  Channel-parameterised kernels use a 2-D block:
+// threadIdx.x = channel vector (fixed for the thread's lifetime, so per-channel parameters live in
+// registers), threadIdx.y = row lane; a block walks a contiguous slab of rows, 2 rows in flight per
+// thread.  Memory is touched in fully contiguous runs of Cp elements per row.
 // ---------------------------------------------------------------------------------------------------
-constexpr int STAT_ROWS_PER_BLOCK = 256;
+struct F8 { float v[8]; };
 
-template <typename T, int MODE>  // MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce (in place g)
+template <typename T> __device__ __forceinline__ F8 ld8(const T* p);
+template <> __device__ __forceinline__ F8 ld8<float>(const float* p) {
+  F8 r;
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <> __device__ __forceinline__ F8 ld8<__nv_bfloat16>(const __nv_bfloat16* p) {
+  F8 r;
+  uint4 q = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const F8& r);
+template <> __device__ __forceinline__ void st8<float>(float* p, const F8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const F8& r) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ F8 ldp8(const float* p) { return ld8<float>(p); }
+
+constexpr int ROWS_PER_BLOCK = 128;   // rows of the slab one block walks
+
+// MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce (g written in place over x)
+template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ ss, double* __restrict__ out,
                  int64_t rows, int Cp) {
-  __shared__ float4 sA[8][32], sB[8][32];
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  const int c = (blockIdx.x * 32 + tx) * 4;
-  const int64_t r0 = (int64_t)blockIdx.y * STAT_ROWS_PER_BLOCK;
-  const int64_t r1 = min(rows, r0 + STAT_ROWS_PER_BLOCK);
-  float4 a = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
-  if (c < Cp) {
-    float4 sc, sh, mu, is;
+  extern __shared__ float red_smem[];   // [blockDim.y][Cp] x 2
+  const int cv = threadIdx.x, c = cv * 8, ry = threadIdx.y, R = blockDim.y;
+  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
+  const int64_t r1 = min(rows, r0 + ROWS_PER_BLOCK);
+  F8 a, q;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.v[i] = q.v[i] = 0.f;
+  F8 sc, sh, mu, is;
+  if (MODE == 1) { sc = ldp8(ss + c); sh = ldp8(ss + Cp + c); mu = ldp8(ss + 2 * Cp + c); is = ldp8(ss + 3 * Cp + c); }
+  for (int64_t r = r0 + ry; r < r1; r += 2 * R) {
+    const bool two = r + R < r1;
+    F8 v0 = ld8<T>(x + r * Cp + c), v1, y0, y1;
+    if (two) v1 = ld8<T>(x + (r + R) * Cp + c);
     if (MODE == 1) {
-      sc = *reinterpret_cast<const float4*>(ss + c);
-      sh = *reinterpret_cast<const float4*>(ss + Cp + c);
-      mu = *reinterpret_cast<const float4*>(ss + 2 * Cp + c);
-      is = *reinterpret_cast<const float4*>(ss + 3 * Cp + c);
+      y0 = ld8<T>(y + r * Cp + c);
+      if (two) y1 = ld8<T>(y + (r + R) * Cp + c);
     }
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      float4 v = Vec4<T>::ld(x + r * Cp + c);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      F8& v = h ? v1 : v0;
       if (MODE == 0) {
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a.v[i] += v.v[i]; q.v[i] += v.v[i] * v.v[i]; }
       } else {
-        float4 yy = Vec4<T>::ld(y + r * Cp + c);
-        float4 g;
-        g.x = v.x * gelu_grad_f(yy.x * sc.x + sh.x);
-        g.y = v.y * gelu_grad_f(yy.y * sc.y + sh.y);
-        g.z = v.z * gelu_grad_f(yy.z * sc.z + sh.z);
-        g.w = v.w * gelu_grad_f(yy.w * sc.w + sh.w);
-        Vec4<T>::st(x + r * Cp + c, g);
-        a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
-        q.x += g.x * (yy.x - mu.x) * is.x; q.y += g.y * (yy.y - mu.y) * is.y;
-        q.z += g.z * (yy.z - mu.z) * is.z; q.w += g.w * (yy.w - mu.w) * is.w;
+        const F8& yy = h ? y1 : y0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float g = v.v[i] * gelu_grad_f(yy.v[i] * sc.v[i] + sh.v[i]);
+          v.v[i] = g;
+          a.v[i] += g;
+          q.v[i] += g * (yy.v[i] - mu.v[i]) * is.v[i];
+        }
+        st8<T>(x + (r + (h ? R : 0)) * Cp + c, v);
       }
     }
   }
-  sA[ty][tx] = a; sB[ty][tx] = q;
-  __syncthreads();
-  if (ty == 0 && c < Cp) {
+  float* sa = red_smem;
+  float* sq = red_smem + R * Cp;
 #pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      float4 u = sA[i][tx], w = sB[i][tx];
-      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
-      q.x += w.x; q.y += w.y; q.z += w.z; q.w += w.w;
-    }
-    atomicAdd(out + c + 0, (double)a.x); atomicAdd(out + c + 1, (double)a.y);
-    atomicAdd(out + c + 2, (double)a.z); atomicAdd(out + c + 3, (double)a.w);
-    atomicAdd(out + Cp + c + 0, (double)q.x); atomicAdd(out + Cp + c + 1, (double)q.y);
-    atomicAdd(out + Cp + c + 2, (double)q.z); atomicAdd(out + Cp + c + 3, (double)q.w);
+  for (int i = 0; i < 8; ++i) { sa[ry * Cp + c + i] = a.v[i]; sq[ry * Cp + c + i] = q.v[i]; }
+  __syncthreads();
+  const int tid = ry * blockDim.x + cv, nthreads = blockDim.x * R;
+  for (int ch = tid; ch < Cp; ch += nthreads) {
+    float ta = 0.f, tq = 0.f;
+    for (int k = 0; k < R; ++k) { ta += sa[k * Cp + ch]; tq += sq[k * Cp + ch]; }
+    atomicAdd(out + ch, (double)ta);
+    atomicAdd(out + Cp + ch, (double)tq);
   }
 }
 
@@ -207,56 +249,66 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, int 
 }
 
 template <typename T>
-__global__ void bn_gelu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss, T* __restrict__ u,
-                                   int64_t n4, int Cp) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t step = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n4; i += step) {
-    int c = (int)((i * 4) % Cp);
-    float4 sc = *reinterpret_cast<const float4*>(ss + c);
-    float4 sh = *reinterpret_cast<const float4*>(ss + Cp + c);
-    float4 v = Vec4<T>::ld(y + i * 4);
-    v.x = gelu_f(v.x * sc.x + sh.x); v.y = gelu_f(v.y * sc.y + sh.y);
-    v.z = gelu_f(v.z * sc.z + sh.z); v.w = gelu_f(v.w * sc.w + sh.w);
-    Vec4<T>::st(u + i * 4, v);
+__global__ void __launch_bounds__(256)
+bn_gelu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss, T* __restrict__ u, int64_t rows, int Cp) {
+  const int c = threadIdx.x * 8, ry = threadIdx.y, R = blockDim.y;
+  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK, r1 = min(rows, r0 + ROWS_PER_BLOCK);
+  const F8 sc = ldp8(ss + c), sh = ldp8(ss + Cp + c);
+  for (int64_t r = r0 + ry; r < r1; r += 2 * R) {
+    const bool two = r + R < r1;
+    F8 v0 = ld8<T>(y + r * Cp + c), v1;
+    if (two) v1 = ld8<T>(y + (r + R) * Cp + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v0.v[i] = gelu_f(v0.v[i] * sc.v[i] + sh.v[i]);
+    st8<T>(u + r * Cp + c, v0);
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v1.v[i] = gelu_f(v1.v[i] * sc.v[i] + sh.v[i]);
+      st8<T>(u + (r + R) * Cp + c, v1);
+    }
   }
 }
 
 // dy = scale * (g - sum_g/n - xhat * sum_gx/n)
 template <typename T>
-__global__ void bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ ss,
-                                    const double* __restrict__ red, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int64_t rows, int64_t n_stat, int C, int Cp, int training) {
-  const int64_t n4 = rows * Cp / 4;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t step = (int64_t)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ ss,
+                    const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    int64_t rows, int64_t n_stat, int C, int Cp, int training) {
+  const int c = threadIdx.x * 8, ry = threadIdx.y, R = blockDim.y;
+  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK, r1 = min(rows, r0 + ROWS_PER_BLOCK);
   if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dbeta) dbeta[c] = (float)red[c];
-      if (dgamma) dgamma[c] = (float)red[Cp + c];
+    const int tid = ry * blockDim.x + threadIdx.x;
+    for (int ch = tid; ch < C; ch += blockDim.x * R) {
+      if (dbeta) dbeta[ch] = (float)red[ch];
+      if (dgamma) dgamma[ch] = (float)red[Cp + ch];
     }
   }
+  const F8 sc = ldp8(ss + c), mu = ldp8(ss + 2 * Cp + c), is = ldp8(ss + 3 * Cp + c);
   const float invn = 1.0f / (float)n_stat;
-  for (; i < n4; i += step) {
-    int c = (int)((i * 4) % Cp);
-    float4 sc = *reinterpret_cast<const float4*>(ss + c);
-    float4 v = Vec4<T>::ld(g + i * 4);
+  F8 sg, sx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sg.v[i] = (float)red[c + i] * invn; sx.v[i] = (float)red[Cp + c + i] * invn; }
+  for (int64_t r = r0 + ry; r < r1; r += 2 * R) {
+    const bool two = r + R < r1;
+    F8 v0 = ld8<T>(g + r * Cp + c), v1, y0, y1;
+    if (two) v1 = ld8<T>(g + (r + R) * Cp + c);
     if (training) {
-      float4 mu = *reinterpret_cast<const float4*>(ss + 2 * Cp + c);
-      float4 is = *reinterpret_cast<const float4*>(ss + 3 * Cp + c);
-      float4 yy = Vec4<T>::ld(y + i * 4);
-      float sg0 = (float)red[c] * invn, sg1 = (float)red[c + 1] * invn, sg2 = (float)red[c + 2] * invn,
-            sg3 = (float)red[c + 3] * invn;
-      float sx0 = (float)red[Cp + c] * invn, sx1 = (float)red[Cp + c + 1] * invn,
-            sx2 = (float)red[Cp + c + 2] * invn, sx3 = (float)red[Cp + c + 3] * invn;
-      v.x = sc.x * (v.x - sg0 - (yy.x - mu.x) * is.x * sx0);
-      v.y = sc.y * (v.y - sg1 - (yy.y - mu.y) * is.y * sx1);
-      v.z = sc.z * (v.z - sg2 - (yy.z - mu.z) * is.z * sx2);
-      v.w = sc.w * (v.w - sg3 - (yy.w - mu.w) * is.w * sx3);
-    } else {
-      v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+      y0 = ld8<T>(y + r * Cp + c);
+      if (two) y1 = ld8<T>(y + (r + R) * Cp + c);
     }
-    Vec4<T>::st(g + i * 4, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v0.v[i] = training ? sc.v[i] * (v0.v[i] - sg.v[i] - (y0.v[i] - mu.v[i]) * is.v[i] * sx.v[i]) : sc.v[i] * v0.v[i];
+    }
+    st8<T>(g + r * Cp + c, v0);
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v1.v[i] = training ? sc.v[i] * (v1.v[i] - sg.v[i] - (y1.v[i] - mu.v[i]) * is.v[i] * sx.v[i]) : sc.v[i] * v1.v[i];
+      }
+      st8<T>(g + (r + R) * Cp + c, v1);
+    }
   }
 }
 
@@ -295,21 +347,66 @@ __global__ void glu_bwd_kernel(const T* __restrict__ dout, const T* __restrict__
   }
 }
 
+// fast paths: D2 % 8 == 0 (so Op == D2, Np == 2*D2): one thread = 8 value channels + their 8 gates
 template <typename T>
-__global__ void gelu_bwd_kernel(T* __restrict__ du, const T* __restrict__ p, int64_t n4) {
+__global__ void __launch_bounds__(256)
+glu_fwd_vec_kernel(const T* __restrict__ y2, T* __restrict__ out, int64_t rows, int D2) {
+  const int nv = D2 >> 3;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = rows * nv, step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += step) {
+    const int64_t r = i / nv;
+    const int c = (int)(i % nv) * 8;
+    F8 a = ld8<T>(y2 + r * 2 * D2 + c), b = ld8<T>(y2 + r * 2 * D2 + D2 + c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.v[k] *= sigmoid_f(b.v[k]);
+    st8<T>(out + r * D2 + c, a);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+glu_bwd_vec_kernel(const T* __restrict__ dout, const T* __restrict__ y2, T* __restrict__ dy2, int64_t rows, int D2) {
+  const int nv = D2 >> 3;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = rows * nv, step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += step) {
+    const int64_t r = i / nv;
+    const int c = (int)(i % nv) * 8;
+    F8 g = ld8<T>(dout + r * D2 + c), a = ld8<T>(y2 + r * 2 * D2 + c), b = ld8<T>(y2 + r * 2 * D2 + D2 + c);
+    F8 da, db;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float sg = sigmoid_f(b.v[k]);
+      da.v[k] = g.v[k] * sg;
+      db.v[k] = g.v[k] * a.v[k] * sg * (1.f - sg);
+    }
+    st8<T>(dy2 + r * 2 * D2 + c, da);
+    st8<T>(dy2 + r * 2 * D2 + D2 + c, db);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(T* __restrict__ du, const T* __restrict__ p, int64_t n8) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t step = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n4; i += step) {
-    float4 v = Vec4<T>::ld(du + i * 4), q = Vec4<T>::ld(p + i * 4);
-    v.x *= gelu_grad_f(q.x); v.y *= gelu_grad_f(q.y); v.z *= gelu_grad_f(q.z); v.w *= gelu_grad_f(q.w);
-    Vec4<T>::st(du + i * 4, v);
+  for (; i < n8; i += step) {
+    F8 v = ld8<T>(du + i * 8), q = ld8<T>(p + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] *= gelu_grad_f(q.v[k]);
+    st8<T>(du + i * 8, v);
   }
 }
 
 static inline int ew_grid(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = 148 * 32;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+// rows handled concurrently by one block of the channel-vector kernels (blockDim = (Cp/8, rows))
+static inline int chan_block_rows(int Cp) {
+  int r = 256 / (Cp / 8);
+  return r < 1 ? 1 : (r > 16 ? 16 : r);
 }
 
 }  // namespace sd
@@ -358,8 +455,10 @@ int sd_pack_weights(const sd_pack_entry* table, int n, void* stream) {
 
 int sd_colstats(const void* x, double* stats, int64_t rows, int Cp, int dtype, void* stream) {
   SD_REQUIRE(Cp % 8 == 0, "sd_colstats: Cp %% 8 != 0");
-  dim3 grid(cdiv(Cp, 128), cdiv(rows, STAT_ROWS_PER_BLOCK)), block(32, 8);
-  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 0><<<grid, block, 0, (cudaStream_t)stream>>>((T*)x, nullptr, nullptr, stats, rows, Cp));
+  SD_REQUIRE(Cp <= 2048, "sd_colstats: Cp too large");
+  dim3 block(Cp / 8, chan_block_rows(Cp));
+  const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
+  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 0><<<cdiv(rows, ROWS_PER_BLOCK), block, smem, (cudaStream_t)stream>>>((T*)x, nullptr, nullptr, stats, rows, Cp));
   return check_launch("colstats");
 }
 
@@ -373,39 +472,51 @@ int sd_bn_finalize(const double* stats, int C, int Cp, int64_t n, const float* g
 }
 
 int sd_bn_gelu_fwd(const void* y, const float* ss, void* u, int64_t rows, int Cp, int dtype, void* stream) {
-  int64_t n4 = rows * Cp / 4;
-  DISPATCH_DTYPE(dtype, bn_gelu_fwd_kernel<T><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)u, n4, Cp));
+  SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_gelu_fwd: bad Cp");
+  dim3 block(Cp / 8, chan_block_rows(Cp));
+  DISPATCH_DTYPE(dtype, bn_gelu_fwd_kernel<T><<<cdiv(rows, ROWS_PER_BLOCK), block, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)u, rows, Cp));
   return check_launch("bn_gelu_fwd");
 }
 
 int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* red, int64_t rows, int Cp, int dtype,
                           void* stream) {
-  dim3 grid(cdiv(Cp, 128), cdiv(rows, STAT_ROWS_PER_BLOCK)), block(32, 8);
-  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1><<<grid, block, 0, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
+  SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_gelu_bwd_reduce: bad Cp");
+  dim3 block(Cp / 8, chan_block_rows(Cp));
+  const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
+  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1><<<cdiv(rows, ROWS_PER_BLOCK), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
   return check_launch("bn_gelu_bwd_reduce");
 }
 
 int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* red, float* dgamma, float* dbeta,
                     int64_t rows, int64_t n_stat, int C, int Cp, int training, int dtype, void* stream) {
-  int64_t n4 = rows * Cp / 4;
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, C, Cp, training));
+  SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_bwd_apply: bad Cp");
+  dim3 block(Cp / 8, chan_block_rows(Cp));
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<cdiv(rows, ROWS_PER_BLOCK), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, C, Cp, training));
   return check_launch("bn_bwd_apply");
 }
 
 int sd_glu_fwd(const void* y2, void* out, int64_t rows, int D2, int Np, int Op, int dtype, void* stream) {
+  if (D2 % 8 == 0 && Np == 2 * D2 && Op == D2) {
+    DISPATCH_DTYPE(dtype, glu_fwd_vec_kernel<T><<<ew_grid(rows * (D2 / 8), 256), 256, 0, (cudaStream_t)stream>>>((const T*)y2, (T*)out, rows, D2));
+    return check_launch("glu_fwd_vec");
+  }
   DISPATCH_DTYPE(dtype, glu_fwd_kernel<T><<<ew_grid(rows * Op, 256), 256, 0, (cudaStream_t)stream>>>((const T*)y2, (T*)out, rows, D2, Np, Op));
   return check_launch("glu_fwd");
 }
 
 int sd_glu_bwd(const void* dout, const void* y2, void* dy2, int64_t rows, int D2, int Np, int Op, int dtype,
                void* stream) {
+  if (D2 % 8 == 0 && Np == 2 * D2 && Op == D2) {
+    DISPATCH_DTYPE(dtype, glu_bwd_vec_kernel<T><<<ew_grid(rows * (D2 / 8), 256), 256, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)y2, (T*)dy2, rows, D2));
+    return check_launch("glu_bwd_vec");
+  }
   DISPATCH_DTYPE(dtype, glu_bwd_kernel<T><<<ew_grid(rows * Np, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)y2, (T*)dy2, rows, D2, Np, Op));
   return check_launch("glu_bwd");
 }
 
 int sd_gelu_bwd(void* du_dp, const void* p, int64_t rows, int Cp, int dtype, void* stream) {
-  int64_t n4 = rows * Cp / 4;
-  DISPATCH_DTYPE(dtype, gelu_bwd_kernel<T><<<ew_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>((T*)du_dp, (const T*)p, n4));
+  int64_t n8 = rows * Cp / 8;
+  DISPATCH_DTYPE(dtype, gelu_bwd_kernel<T><<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>((T*)du_dp, (const T*)p, n8));
   return check_launch("gelu_bwd");
 }
 

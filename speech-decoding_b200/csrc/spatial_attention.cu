@@ -27,11 +27,24 @@ sa_weights_fwd_kernel(const float* __restrict__ z_ri, const float* __restrict__ 
   }
   for (int i = tid; i < 2 * K2; i += blockDim.x) zs[i] = z_ri[(size_t)d * 2 * K2 + i];
   __syncthreads();
+  // logits: the K^2-long contraction is split over the 8 warps (fp64 partial sums, combined in smem);
+  // lanes run over sensors so the cos/sin reads are coalesced.
+  double* part = reinterpret_cast<double*>(smem + 2 * K2 + ((C + 1) & ~1));   // [8][C]
+  {
+    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    const int m0 = (int)((long long)K2 * warp / nw), m1 = (int)((long long)K2 * (warp + 1) / nw);
+    for (int c = lane; c < C; c += 32) {
+      double acc = 0.0;
+      for (int m = m0; m < m1; ++m)
+        acc += (double)zs[2 * m] * (double)cos_t[(size_t)m * C + c] + (double)zs[2 * m + 1] * (double)sin_t[(size_t)m * C + c];
+      part[warp * C + c] = acc;
+    }
+  }
+  __syncthreads();
   float lmax = -INFINITY;
   for (int c = tid; c < C; c += blockDim.x) {
     double acc = 0.0;
-    for (int m = 0; m < K2; ++m)
-      acc += (double)zs[2 * m] * (double)cos_t[(size_t)m * C + c] + (double)zs[2 * m + 1] * (double)sin_t[(size_t)m * C + c];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += part[w * C + c];
     logit[c] = (float)acc;
     lmax = fmaxf(lmax, (float)acc);
   }
@@ -110,7 +123,7 @@ extern "C" {
 
 int sd_sa_weights_fwd(const float* z_ri, const float* cos_t, const float* sin_t, const float* mask, float* w_soft,
                       void* w_packed, int D1, int K2, int C, int D1p, int Cp, int dtype, void* stream) {
-  size_t smem = (size_t)(2 * K2 + C) * sizeof(float);
+  size_t smem = (size_t)(2 * K2 + ((C + 1) & ~1)) * sizeof(float) + (size_t)8 * C * sizeof(double);
   SD_REQUIRE(smem <= 200 * 1024, "sd_sa_weights_fwd: K^2/C too large for shared memory");
   if (dtype == SD_F32) {
     if (smem > 48 * 1024) SD_CUDA(cudaFuncSetAttribute(sa_weights_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

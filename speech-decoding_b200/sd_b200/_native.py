@@ -62,7 +62,7 @@ SIGNATURES = {
     "sd_clip_dots": [vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_phase1": [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
     "sd_clip_phase2": [vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, vp, i32, i32, vp],
-    "sd_clip_dz": [vp, vp, vp, vp, vp, i32, i32, i64, vp],
+    "sd_clip_dz": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
 }
 
 _lib = None

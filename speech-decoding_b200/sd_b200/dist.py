@@ -75,25 +75,17 @@ class GradReducer:
         self.group = group
         self.pending = []
 
-    def stage_done(self, grads):
-        """grads: {param: tensor} produced by one stage.  Launch one coalesced
-        asynchronous all-reduce for them."""
-        tensors = [g for g in grads.values() if g is not None]
-        if not tensors:
+    def stage_done(self, flat, lo, hi):
+        """All-reduce flat[lo:hi] (one stage's parameter gradients, contiguous in the GradPool --
+        absent subjects included as zeros, so the message size is the same on every rank)."""
+        if hi <= lo:
             return
-        flat = torch.cat([torch.view_as_real(t).reshape(-1) if t.is_complex() else t.reshape(-1) for t in tensors])
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self.pending.append((work, flat, tensors))
+        work = dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.pending.append(work)
 
     def finish(self):
-        for work, flat, tensors in self.pending:
+        for work in self.pending:
             work.wait()
-            off = 0
-            for t in tensors:
-                v = torch.view_as_real(t) if t.is_complex() else t
-                n = v.numel()
-                v.copy_(flat[off:off + n].view_as(v))
-                off += n
         self.pending = []
 
 

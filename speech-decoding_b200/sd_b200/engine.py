@@ -71,10 +71,61 @@ class WeightPack:
         return self.bufs[name][1]
 
 
+class GradPool:
+    """One flat fp32 buffer for every parameter gradient of a pipeline (densely packed in parameter
+    order): a single memset per backward instead of one per tensor, and data-parallel all-reduces can
+    work on contiguous slices.  Gradients handed to autograd are views into it."""
+
+    def __init__(self, params):
+        self.offsets = {}
+        off = 0
+        for p in params:
+            n = p.numel() * (2 if p.is_complex() else 1)
+            self.offsets[p] = (off, n)
+            off += n
+        self.total = off
+        self.flat = None
+
+    def new(self, device):
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+
+    def view(self, p):
+        off, n = self.offsets[p]
+        t = self.flat[off:off + n]
+        return t.view(*p.shape, 2) if p.is_complex() else t.view(p.shape)
+
+    def stacked(self, params):
+        """(len(params), *shape) view over consecutive same-shaped parameters."""
+        off0, n = self.offsets[params[0]]
+        for i, p in enumerate(params):
+            assert self.offsets[p] == (off0 + i * n, n), "parameters are not consecutive in the pool"
+        return self.flat[off0:off0 + n * len(params)].view(len(params), *params[0].shape)
+
+    def span(self, params):
+        lo = min(self.offsets[p][0] for p in params)
+        hi = max(self.offsets[p][0] + self.offsets[p][1] for p in params)
+        return lo, hi
+
+
+class ScratchPool:
+    """Bump allocator over one zero-filled fp64 buffer (BatchNorm statistics / reduction scratch)."""
+
+    def __init__(self, n, device):
+        self.buf = torch.zeros(max(n, 1), dtype=torch.float64, device=device)
+        self.off = 0
+
+    def take(self, n):
+        t = self.buf[self.off:self.off + n]
+        self.off += n
+        return t
+
+
 # --------------------------------------------------------------------------------------------------
 # stages
 # --------------------------------------------------------------------------------------------------
 class Stage:
+    scratch = 0          # fp64 scratch elements needed per forward / backward
+
     def params(self):
         return []
 
@@ -115,7 +166,8 @@ class SpatialAttentionStage(Stage):
                                       "(the reference never needs it: train.py:187-203)")
         dwm = torch.zeros((D1, C), dtype=torch.float32, device=dout.device)
         ops.conv_wgrad(dout, sv["Xt"], dwm, K=C, N=D1, strides=(0, C, 1, 0))
-        dz = ops.sa_weights_bwd(dwm, sv["w_soft"], sv["mask"], m.cos, m.sin, K2)
+        dz = run.gpool.view(m.z)
+        ops.sa_weights_bwd(dwm, sv["w_soft"], sv["mask"], m.cos, m.sin, K2, out=dz)
         grads[m.z] = torch.view_as_complex(dz)
         return None
 
@@ -162,15 +214,14 @@ class SubjectStage(Stage):
     def backward(self, run, sv, dout, grads, need_dx):
         m = self.m
         D1, S = m.D1, len(m.subject_layer)
-        dws = torch.zeros((S, D1, D1, 1), dtype=torch.float32, device=dout.device)
+        dws = run.gpool.stacked([l.weight for l in m.subject_layer])
         ops.conv_wgrad(dout, sv["h1"], dws, K=D1, N=D1, order=sv["order"], offsets=sv["offsets"], G=S,
                        strides=(D1 * D1, D1, 1, 0))
         for s in sv["present"]:                      # absent subjects keep grad None
             grads[m.subject_layer[int(s)].weight] = dws[int(s)]
         dh1 = torch.empty_like(dout)
         ops.conv_fwd(dout, run.pack.wd(self.key + ".subj"), K=D1, N=D1, widx=sv["widx"], G=S, out=dh1)
-        dwc = torch.zeros_like(m.conv.weight)
-        dbc = torch.zeros_like(m.conv.bias)
+        dwc, dbc = run.gpool.view(m.conv.weight), run.gpool.view(m.conv.bias)
         ops.conv_wgrad(dh1, sv["x"], dwc, K=D1, N=D1, dbias=dbc)
         grads[m.conv.weight], grads[m.conv.bias] = dwc, dbc
         dx = torch.empty_like(dout)
@@ -180,6 +231,10 @@ class SubjectStage(Stage):
 
 class ConvBlockStage(Stage):
     """models.py:152-166."""
+
+    @property
+    def scratch(self):
+        return 4 * rup8(self.m.D2)
 
     def __init__(self, blk):
         self.m = blk
@@ -215,7 +270,7 @@ class ConvBlockStage(Stage):
         d0, d1 = m.conv0.dilation[0], m.conv1.dilation[0]
         dev, dt = x.device, run.dtype
         train = m.batchnorm0.training
-        stats = torch.zeros((2, 2 * D2p), dtype=torch.float64, device=dev) if train else None
+        stats = run.scratch.take(4 * D2p).view(2, 2 * D2p) if train else None
         ss = torch.empty((2, 4 * D2p), dtype=torch.float32, device=dev)
         y0 = torch.empty((B, T, D2p), dtype=dt, device=dev)
         ops.conv_fwd(x, run.pack.wf(self.key + ".c0"), K=Cin, N=D2, taps=3, dil=d0, bias=m.conv0.bias,
@@ -244,10 +299,8 @@ class ConvBlockStage(Stage):
         d0, d1, d2 = m.conv0.dilation[0], m.conv1.dilation[0], m.conv2.dilation[0]
         dev = dout.device
         ss, train = sv["ss"], sv["train"]
-        red = torch.zeros((2, 2 * D2p), dtype=torch.float64, device=dev)
-
-        def zl(p):
-            return torch.zeros_like(p)
+        red = run.scratch.take(4 * D2p).view(2, 2 * D2p)
+        zl = run.gpool.view
 
         # conv2 + GLU
         dy2 = torch.empty_like(sv["y2"])
@@ -321,13 +374,13 @@ class FinalStage(Stage):
         N1, Fo = 2 * m.D2, m.F
         dZ = dZ.contiguous().float()
         dp2 = ops.gelu_bwd_nct(dZ, sv["p2"], Fo)
-        dw2, db2 = torch.zeros_like(m.conv_final2.weight), torch.zeros_like(m.conv_final2.bias)
+        dw2, db2 = run.gpool.view(m.conv_final2.weight), run.gpool.view(m.conv_final2.bias)
         ops.conv_wgrad(dp2, sv["u"], dw2, K=N1, N=Fo, dbias=db2)
         du = torch.empty_like(sv["u"])
         ops.conv_fwd(dp2, run.pack.wd(self.key + ".f2"), K=Fo, N=N1, out=du)
         del dp2
         ops.gelu_bwd(du, sv["p1"])
-        dw1, db1 = torch.zeros_like(m.conv_final1.weight), torch.zeros_like(m.conv_final1.bias)
+        dw1, db1 = run.gpool.view(m.conv_final1.weight), run.gpool.view(m.conv_final1.bias)
         ops.conv_wgrad(du, sv["x"], dw1, K=m.D2, N=N1, dbias=db1)
         grads.update({m.conv_final2.weight: dw2, m.conv_final2.bias: db2,
                       m.conv_final1.weight: dw1, m.conv_final1.bias: db1})
@@ -374,6 +427,9 @@ class Pipeline:
             s.register(self.pack)
         self.subject_ids = None
         self.dtype = None
+        self.gpool = None
+        self.scratch = None
+        self._scratch_n = sum(st.scratch for st in stages)
         self.reducer = None         # dist.GradReducer: per-stage gradient all-reduce (data parallel)
         self.bn_group = None        # process group for SyncBN statistics, or None
         self.host_group = None      # gloo side channel for host-side metadata
@@ -402,6 +458,7 @@ class Pipeline:
         self.dtype = ops.dtypes()[0]
         self.pack.refresh(X.device, self.dtype)
         saved = [dict() if keep else None for _ in self.stages]
+        self.scratch = ScratchPool(self._scratch_n, X.device)
         h = X
         for s, sv in zip(self.stages, saved):
             h = s.forward(self, h, sv)
@@ -411,12 +468,18 @@ class Pipeline:
         grads = {}
         g = dout
         n = len(self.stages)
+        params = self.params()
+        if self.gpool is None or set(self.gpool.offsets) != set(params):
+            self.gpool = GradPool(params)
+        self.gpool.new(dout.device)
+        self.scratch = ScratchPool(self._scratch_n, dout.device)
         for i in range(n - 1, -1, -1):
             sg = {}
             g = self.stages[i].backward(self, saved[i], g, sg, need_dx or i > 0)
             saved[i] = None          # release activations as we go
-            if self.reducer is not None:
-                self.reducer.stage_done(sg)      # async all-reduce overlaps the remaining backward
+            if self.reducer is not None and self.stages[i].params():
+                # async all-reduce of this stage's contiguous slice overlaps the remaining backward
+                self.reducer.stage_done(self.gpool.flat, *self.gpool.span(self.stages[i].params()))
             grads.update(sg)
         if self.reducer is not None:
             self.reducer.finish()

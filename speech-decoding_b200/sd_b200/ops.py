@@ -150,9 +150,9 @@ def sa_weights_fwd(z_ri, cos, sin, mask, D1, K2, C, dtype):
     return w_soft, w_packed
 
 
-def sa_weights_bwd(dwm, w_soft, mask, cos, sin, K2):
+def sa_weights_bwd(dwm, w_soft, mask, cos, sin, K2, out=None):
     D1, C = w_soft.shape
-    dz = torch.empty((D1, K2, 2), dtype=torch.float32, device=dwm.device)
+    dz = out if out is not None else torch.empty((D1, K2, 2), dtype=torch.float32, device=dwm.device)
     nat.call("sd_sa_weights_bwd", _p(dwm), _p(w_soft), _p(mask), _p(cos), _p(sin), _p(dz), D1, K2, C, _st())
     return dz
 
@@ -193,9 +193,9 @@ def clip_phase2(logits, row_lse, col_lse, xn2, zn2, temp, scale, diag0):
     return coef, cz, partial
 
 
-def clip_dz(coef, cz, x2d, z2d):
+def clip_dz(coef, cz, x2d, z2d, gscale=None):
     M, D = x2d.shape
     Nn = z2d.shape[0]
     dz = torch.empty((Nn, D), dtype=torch.float32, device=x2d.device)
-    nat.call("sd_clip_dz", _p(coef), _p(cz), _p(x2d), _p(z2d), _p(dz), M, Nn, D, _st())
+    nat.call("sd_clip_dz", _p(coef), _p(cz), _p(x2d), _p(z2d), _p(dz), _p(gscale), M, Nn, D, _st())
     return dz

@@ -66,14 +66,12 @@ class _ClipFn(torch.autograd.Function):
         dx = dz = dtemp = None
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[1]:
-                dz = ops.clip_dz(coef, cz, x, z)
-                dz.mul_(gloss)
+                dz = ops.clip_dz(coef, cz, x, z, gloss.detach().float().reshape(1).contiguous())
             if ctx.needs_input_grad[0]:
                 # symmetric formula for the speech side (appendix A.5); rarely needed (Y carries no grad)
                 gl = coef * logits * (xn2.sqrt()[:, None] * zn2.sqrt()[None, :]) / torch.exp(t)
                 cx = gl.sum(dim=1) / xn2
-                dx = ops.clip_dz(coef.t().contiguous(), cx.contiguous(), z, x)
-                dx.mul_(gloss)
+                dx = ops.clip_dz(coef.t().contiguous(), cx.contiguous(), z, x, gloss.detach().float().reshape(1).contiguous())
             if ctx.needs_input_grad[2] and ctx.use_temp:
                 dtemp = (partial[1] * gloss).reshape(1)
         return dx, dz, dtemp, None, None, None
