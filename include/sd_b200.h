@@ -171,14 +171,23 @@ int sd_clip_phase1(const float* dots, const float* xn2, const float* zn2, const 
  *   G = d loss / d logits = scale/2 * (softmax_rows + softmax_cols - 2*I), I at (diag0 + j, j)
  *   coef[i,j] = exp(temp) * G[i,j] / (|x_i||z_j|);  cz[j] = (sum_i G*logits)[j] / |z_j|^2
  *   partial[0] += this rank's share of the loss, partial[1] += sum G*logits (= d loss / d temp)
- *   scale = 1/M_global for reduction="mean", 1 for "sum" (loss.py:32,79). */
+ *   scale = 1/M_global for reduction="mean", 1 for "sum" (loss.py:32,79).
+ *   coef_t (N, roundup4(M)) or NULL: the same coefficients transposed (A operand of sd_clip_dz_tc). */
 int sd_clip_phase2(const float* logits, const float* row_lse, const float* col_lse, const float* xn2,
-                   const float* zn2, const float* temp, float scale, int diag0, float* coef, float* cz,
+                   const float* zn2, const float* temp, float scale, int diag0, float* coef, float* coef_t, float* cz,
                    float* partial, int M, int N, void* stream);
 /* dz[j,d] = gscale * (sum_i coef[i,j] * x[i,d] - cz[j] * z[j,d])   (appendix A.5);
  * gscale: device pointer to the upstream gradient of the scalar loss, or NULL (= 1) */
 int sd_clip_dz(const float* coef, const float* cz, const float* x, const float* z, float* dz, const float* gscale,
                int M, int N, int64_t D, void* stream);
+
+/* Tensor-core (tcgen05 kind::tf32, operands read as fp32 by TMA) forms of the two streaming GEMMs, used by
+ * the bf16 mode.  Need D % 4 == 0.  workspace: sd_clip_dots_workspace_bytes() bytes (split-K partials). */
+int64_t sd_clip_dots_workspace_bytes(int M, int N, int64_t D);
+int sd_clip_dots_tc(const float* x, const float* z, float* dots, void* workspace, int M, int N, int64_t D,
+                    void* stream);
+int sd_clip_dz_tc(const float* coef_t, const float* cz, const float* x, const float* z, float* dz,
+                  const float* gscale, int M, int N, int64_t D, void* stream);
 
 #ifdef __cplusplus
 }

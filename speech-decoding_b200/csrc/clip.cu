@@ -161,8 +161,8 @@ clip_cols_kernel(const float* __restrict__ logits, float* __restrict__ col_lse, 
 __global__ void __launch_bounds__(256)
 clip_grad_kernel(const float* __restrict__ logits, const float* __restrict__ row_lse, const float* __restrict__ col_lse,
                  const float* __restrict__ xn2, const float* __restrict__ zn2, const float* __restrict__ temp,
-                 float scale, int diag0, float* __restrict__ coef, float* __restrict__ cz, float* __restrict__ partial,
-                 int M, int N) {
+                 float scale, int diag0, float* __restrict__ coef, float* __restrict__ coef_t, float* __restrict__ cz,
+                 float* __restrict__ partial, int M, int N) {
   __shared__ float red[8];
   const int i = blockIdx.x, tid = threadIdx.x;
   const float rl = row_lse[i];
@@ -171,7 +171,9 @@ clip_grad_kernel(const float* __restrict__ logits, const float* __restrict__ row
   for (int j = tid; j < N; j += 256) {
     float l = logits[(size_t)i * N + j];
     float g = 0.5f * scale * (expf(l - rl) + expf(l - col_lse[j]) - ((i == diag0 + j) ? 2.f : 0.f));
-    coef[(size_t)i * N + j] = g * sx * rsqrtf(zn2[j]);
+    const float cf = g * sx * rsqrtf(zn2[j]);
+    coef[(size_t)i * N + j] = cf;
+    if (coef_t) coef_t[(size_t)j * ((M + 3) & ~3) + i] = cf;
     float gl = g * l;
     gl_sum += gl;
     atomicAdd(cz + j, gl / zn2[j]);
@@ -246,9 +248,35 @@ clip_dz_kernel(const float* __restrict__ coef, const float* __restrict__ cz, con
 
 }  // namespace sd
 
+namespace sd {
+bool clip_tc_supported(int M, int N, int64_t D, const void* x, const void* z);
+size_t clip_dots_tc_workspace(int M, int N, int64_t D);
+int clip_dots_tc(const float* x, const float* z, float* dots, float* workspace, int M, int N, int64_t D, cudaStream_t st);
+int clip_dz_tc(const float* coef_t, const float* cz, const float* x, const float* z, float* dz, const float* gscale,
+               int M, int N, int64_t D, cudaStream_t st);
+}  // namespace sd
+
 using namespace sd;
 
 extern "C" {
+
+int64_t sd_clip_dots_workspace_bytes(int M, int N, int64_t D) {
+  if (D % 4 != 0 || D < 64) return 0;
+  return (int64_t)clip_dots_tc_workspace(M, N, D);
+}
+
+int sd_clip_dots_tc(const float* x, const float* z, float* dots, void* workspace, int M, int N, int64_t D, void* stream) {
+  SD_REQUIRE(clip_tc_supported(M, N, D, x, z), "sd_clip_dots_tc: unsupported shape/alignment (D %% 4 != 0?)");
+  SD_REQUIRE(workspace != nullptr, "sd_clip_dots_tc: workspace is null");
+  return clip_dots_tc(x, z, dots, reinterpret_cast<float*>(workspace), M, N, D, (cudaStream_t)stream);
+}
+
+int sd_clip_dz_tc(const float* coef_t, const float* cz, const float* x, const float* z, float* dz, const float* gscale,
+                  int M, int N, int64_t D, void* stream) {
+  SD_REQUIRE(clip_tc_supported(M, N, D, x, z), "sd_clip_dz_tc: unsupported shape/alignment (D %% 4 != 0?)");
+  SD_REQUIRE(coef_t != nullptr && (((uintptr_t)dz) & 15) == 0, "sd_clip_dz_tc: bad pointers");
+  return clip_dz_tc(coef_t, cz, x, z, dz, gscale, M, N, D, (cudaStream_t)stream);
+}
 
 int sd_rownorm2(const float* x, float* nrm2, int M, int64_t D, void* stream) {
   return rownorm2_launch(x, nrm2, M, D, 0, (cudaStream_t)stream);
@@ -273,12 +301,12 @@ int sd_clip_phase1(const float* dots, const float* xn2, const float* zn2, const 
 }
 
 int sd_clip_phase2(const float* logits, const float* row_lse, const float* col_lse, const float* xn2,
-                   const float* zn2, const float* temp, float scale, int diag0, float* coef, float* cz,
+                   const float* zn2, const float* temp, float scale, int diag0, float* coef, float* coef_t, float* cz,
                    float* partial, int M, int N, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SD_CUDA(cudaMemsetAsync(cz, 0, sizeof(float) * N, st));
   SD_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * 2, st));
-  clip_grad_kernel<<<M, 256, 0, st>>>(logits, row_lse, col_lse, xn2, zn2, temp, scale, diag0, coef, cz, partial, M, N);
+  clip_grad_kernel<<<M, 256, 0, st>>>(logits, row_lse, col_lse, xn2, zn2, temp, scale, diag0, coef, coef_t, cz, partial, M, N);
   return check_launch("clip_grad");
 }
 

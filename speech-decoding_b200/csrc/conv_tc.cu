@@ -467,7 +467,8 @@ EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                 CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = encode_fn();
   SD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -475,7 +476,7 @@ int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint6
   cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u",
              (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
              (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, box0, box1, box2);

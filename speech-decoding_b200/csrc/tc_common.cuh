@@ -18,7 +18,8 @@ EncodeTiledFn encode_fn();
 // rank-3 tiled map with 128-byte swizzle and zero OOB fill. dims/strides innermost first; strides in bytes
 // for dims 1..2 (dim 0 is contiguous).
 int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 // ---- device: barriers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,13 +139,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major operand (rows of 64 bf16 = 128 B, 8-row groups of 1024 B): SBO = 1024, LBO unused.
 // MN-major operand (128 B of 64 contiguous MN elements per K row; 8 K rows = 1024 B):
 //   SBO = 1024 (next 8 K rows), LBO = byte distance between 64-element MN blocks.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// 32-bit MN-major operands (tf32) must use the 128B-swizzle-with-32B-atoms layout (type 1, TMA mode
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 128 B of 32 contiguous MN elements per K row, the pattern repeats
+// every 4 K rows, so SBO = 512 (cutlass sm100_common.inl: "SW128_32B is the only available smem layout").
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 

@@ -61,7 +61,10 @@ SIGNATURES = {
     "sd_rownorm2": [vp, vp, i32, i64, vp],
     "sd_clip_dots": [vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_phase1": [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
-    "sd_clip_phase2": [vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, vp, i32, i32, vp],
+    "sd_clip_phase2": [vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, i32, i32, vp],
+    "sd_clip_dots_workspace_bytes": [i32, i32, i64],
+    "sd_clip_dots_tc": [vp, vp, vp, vp, i32, i32, i64, vp],
+    "sd_clip_dz_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_dz": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
 }
 
@@ -82,7 +85,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = i32
+            fn.restype = i64 if name == "sd_clip_dots_workspace_bytes" else i32
         _lib = l
     return _lib
 

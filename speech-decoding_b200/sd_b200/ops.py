@@ -165,9 +165,22 @@ def rownorm2(x2d):
     return out
 
 
-def clip_dots(x2d, z2d):
+def clip_tc_ok(x2d, z2d):
+    """tensor-core (TF32) CLIP kernels: used by the bf16 mode when the shape allows TMA"""
+    M, D = x2d.shape
+    return (get_precision() == "bf16" and D % 4 == 0 and D >= 64
+            and nat.lib().sd_clip_dots_workspace_bytes(M, z2d.shape[0], D) > 0)
+
+
+def clip_dots(x2d, z2d, tc=False):
     M, D = x2d.shape
     Nn = z2d.shape[0]
+    if tc:
+        ws_bytes = nat.lib().sd_clip_dots_workspace_bytes(M, Nn, D)
+        ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x2d.device)
+        dots = torch.empty((M, Nn), dtype=torch.float32, device=x2d.device)
+        nat.call("sd_clip_dots_tc", _p(x2d), _p(z2d), _p(dots), _p(ws), M, Nn, D, _st())
+        return dots
     dots = torch.zeros((M, Nn), dtype=torch.float32, device=x2d.device)
     nat.call("sd_clip_dots", _p(x2d), _p(z2d), _p(dots), M, Nn, D, _st())
     return dots
@@ -183,14 +196,25 @@ def clip_phase1(dots, xn2, zn2, temp):
     return logits, row_stat, col_lse
 
 
-def clip_phase2(logits, row_lse, col_lse, xn2, zn2, temp, scale, diag0):
+def clip_phase2(logits, row_lse, col_lse, xn2, zn2, temp, scale, diag0, want_t=False):
     M, Nn = logits.shape
     coef = torch.empty_like(logits)
+    coef_t = torch.zeros((Nn, (M + 3) // 4 * 4), dtype=torch.float32, device=logits.device) if want_t else None
     cz = torch.empty((Nn,), dtype=torch.float32, device=logits.device)
     partial = torch.empty((2,), dtype=torch.float32, device=logits.device)
     nat.call("sd_clip_phase2", _p(logits), _p(row_lse), _p(col_lse), _p(xn2), _p(zn2), _p(temp), scale, diag0,
-             _p(coef), _p(cz), _p(partial), M, Nn, _st())
+             _p(coef), _p(coef_t), _p(cz), _p(partial), M, Nn, _st())
+    if want_t:
+        return coef, coef_t, cz, partial
     return coef, cz, partial
+
+
+def clip_dz_tc(coef_t, cz, x2d, z2d, gscale=None):
+    M, D = x2d.shape
+    Nn = z2d.shape[0]
+    dz = torch.empty((Nn, D), dtype=torch.float32, device=x2d.device)
+    nat.call("sd_clip_dz_tc", _p(coef_t), _p(cz), _p(x2d), _p(z2d), _p(dz), _p(gscale), M, Nn, D, _st())
+    return dz
 
 
 def clip_dz(coef, cz, x2d, z2d, gscale=None):

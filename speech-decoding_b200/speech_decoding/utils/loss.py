@@ -43,30 +43,34 @@ class _ClipFn(torch.autograd.Function):
         M, Nn = x.shape[0], z.shape[0]
         world, rank = sd_dist.world_rank(group)
         with torch.cuda.device(x.device):
+            tc = ops.clip_tc_ok(x, z)          # bf16 mode: TF32 tensor-core GEMMs; fp32 mode: exact fp32
             xn2 = ops.rownorm2(x)
             zn2 = ops.rownorm2(z)
-            dots = ops.clip_dots(x, z)
+            dots = ops.clip_dots(x, z, tc=tc)
             t = temp.detach() if use_temp else torch.zeros_like(temp)
             logits, row_stat, col_lse = ops.clip_phase1(dots, xn2, zn2, t)
             if world > 1:
                 row_stat = sd_dist.merge_row_stats(row_stat, group)
             row_lse = row_stat[:, 0] + torch.log(row_stat[:, 1])
             scale = 1.0 / M if reduction == "mean" else 1.0
-            coef, cz, partial = ops.clip_phase2(logits, row_lse, col_lse, xn2, zn2, t, scale, rank * Nn)
+            coef, coef_t, cz, partial = ops.clip_phase2(logits, row_lse, col_lse, xn2, zn2, t, scale, rank * Nn,
+                                                        want_t=True)
             if world > 1:
                 partial = sd_dist.all_reduce_sum(partial, group)
-        ctx.save_for_backward(x, z, coef, cz, partial, logits, xn2, zn2, t)
+        ctx.save_for_backward(x, z, coef, cz, partial, logits, xn2, zn2, t, coef_t)
         ctx.use_temp = use_temp
+        ctx.tc = tc
         ctx.mark_non_differentiable(logits)
         return partial[0].clone(), logits
 
     @staticmethod
     def backward(ctx, gloss, _glogits):
-        x, z, coef, cz, partial, logits, xn2, zn2, t = ctx.saved_tensors
+        x, z, coef, cz, partial, logits, xn2, zn2, t, coef_t = ctx.saved_tensors
         dx = dz = dtemp = None
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[1]:
-                dz = ops.clip_dz(coef, cz, x, z, gloss.detach().float().reshape(1).contiguous())
+                gs = gloss.detach().float().reshape(1).contiguous()
+                dz = ops.clip_dz_tc(coef_t, cz, x, z, gs) if ctx.tc else ops.clip_dz(coef, cz, x, z, gs)
             if ctx.needs_input_grad[0]:
                 # symmetric formula for the speech side (appendix A.5); rarely needed (Y carries no grad)
                 gl = coef * logits * (xn2.sqrt()[:, None] * zn2.sqrt()[None, :]) / torch.exp(t)

@@ -297,3 +297,32 @@ def test_clip_kernels(M, N, D, diag0):
     assert rel(partial[1], temp.grad[0]) < 1e-3
     dz = ops.clip_dz(coef, cz, x, z.detach())
     assert rel(dz, z.grad) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,D,diag0", [(256, 256, 36864, 0), (64, 48, 4096, 0), (300, 100, 2048, 128), (512, 256, 8192, 256)])
+def test_clip_tensor_core_kernels(M, N, D, diag0):
+    """TF32 tcgen05 forms of the similarity and gradient GEMMs (bf16 mode) against fp32 matmuls."""
+    ops, nat = _ops()
+    torch.manual_seed(9)
+    x = torch.randn(M, D, device=DEV)
+    z = torch.randn(N, D, device=DEV) + 0.3 * x[diag0:diag0 + N]
+    ws = torch.empty(nat.lib().sd_clip_dots_workspace_bytes(M, N, D) // 4, device=DEV)
+    dots = torch.full((M, N), float("nan"), device=DEV)
+    nat.call("sd_clip_dots_tc", x.data_ptr(), z.data_ptr(), dots.data_ptr(), ws.data_ptr(), M, N, D,
+             torch.cuda.current_stream().cuda_stream)
+    ref = x.double() @ z.double().T
+    scale = float((x.norm(dim=1)[:, None] * z.norm(dim=1)[None, :]).max())
+    # the tensor core truncates fp32 -> tf32 (10 mantissa bits): a one-sided ~1e-3 relative bias on the
+    # large (diagonal) entries, random-sign noise elsewhere
+    assert float((dots.double() - ref).abs().max()) / scale < 1.5e-3
+    coef = torch.randn(M, N, device=DEV) / M
+    Mp = (M + 3) // 4 * 4
+    coef_t = torch.zeros(N, Mp, device=DEV)
+    coef_t[:, :M] = coef.T
+    cz = torch.randn(N, device=DEV) * 0.1
+    gs = torch.tensor([0.7], device=DEV)
+    dz0 = ops.clip_dz_tc(coef_t, torch.zeros_like(cz), x, z, None)        # GEMM term alone
+    assert rel(dz0, coef.double().T @ x.double()) < 3e-3
+    dz = ops.clip_dz_tc(coef_t, cz, x, z, gs)
+    ref = 0.7 * (coef.double().T @ x.double() - cz.double()[:, None] * z.double())
+    assert rel(dz, ref) < 3e-3
