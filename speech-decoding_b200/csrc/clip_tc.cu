@@ -74,40 +74,43 @@ clip_dots_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      const uint32_t tx = D_A_BYTES + (uint32_t)p.block_n * 128;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(empty_bar(s), ph ^ 1);
+    int s = 0; uint32_t ph = 0;
+    const uint32_t tx = D_A_BYTES + (uint32_t)p.block_n * 128;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(empty_bar(s), ph ^ 1);
+      if (elect_one_sync()) {
         const uint32_t sa = smem_base + s * D_STAGE_BYTES, sb = sa + D_A_BYTES;
         const int kc = (int)((kb0 + it) * DK);
         mbar_arrive_expect_tx(full_bar(s), tx);
         tma_load_3d(sa, &tmap_x, full_bar(s), kc, m_pair * 256, 0);
         tma_load_3d(sa + 128 * 128, &tmap_x, full_bar(s), kc, m_pair * 256 + 128, 0);
         tma_load_3d(sb, &tmap_z, full_bar(s), kc, n_tile * p.block_n, 0);
-        if (++s == D_STAGES) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == D_STAGES) { s = 0; ph ^= 1; }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(/*tf32*/ 2, 0, 0, 128, (uint32_t)p.block_n);
-      int s = 0; uint32_t ph = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * D_STAGE_BYTES, sb = sa + D_A_BYTES;
+    const uint32_t idesc = make_idesc(/*tf32*/ 2, 0, 0, 128, (uint32_t)p.block_n);
+    const uint32_t dhi = smem_desc_hi(1024);
+    int s = 0; uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t alo = smem_desc_lo(smem_base + s * D_STAGE_BYTES, 16);
+        const uint32_t a2lo = alo + ((128 * 128) >> 4), blo = alo + (D_A_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < DK / 8; ++k) {
-          const uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024);
-          umma_tf32(tmem_base, make_smem_desc(sa + k * 32, 16, 1024), bd, idesc, (it | k) != 0);
-          umma_tf32(tmem_base + 256, make_smem_desc(sa + 128 * 128 + k * 32, 16, 1024), bd, idesc, (it | k) != 0);
+          umma_tf32(tmem_base, desc64(alo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
+          umma_tf32(tmem_base + 256, desc64(a2lo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
         }
         umma_commit(empty_bar(s));
-        if (++s == D_STAGES) { s = 0; ph ^= 1; }
+        if (it == iters - 1) umma_commit(tfull_bar);
       }
-      umma_commit(tfull_bar);
+      __syncwarp();
+      if (++s == D_STAGES) { s = 0; ph ^= 1; }
     }
+    if (iters == 0 && elect_one_sync()) umma_commit(tfull_bar);
     __syncwarp();
   } else {
     const int ew = warp - 2, quad = warp & 3, half = ew >> 2;   // half selects the 128-row accumulator
@@ -203,51 +206,51 @@ clip_dz_tc_kernel(const __grid_constant__ CUtensorMap tmap_ct, const __grid_cons
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int j_tile = tile % p.j_tiles;
-        const long long d0 = (long long)(tile / p.j_tiles) * Z_BN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1);
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int j_tile = tile % p.j_tiles;
+      const long long d0 = (long long)(tile / p.j_tiles) * Z_BN;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (elect_one_sync()) {
           const uint32_t sa = smem_base + s * Z_STAGE_BYTES, sb = sa + Z_A_BYTES;
           mbar_arrive_expect_tx(full_bar(s), Z_STAGE_BYTES);
           tma_load_3d(sa, &tmap_ct, full_bar(s), kb * Z_BK, j_tile * Z_BM, 0);
 #pragma unroll
           for (int a = 0; a < Z_BN / 32; ++a)
             tma_load_3d(sb + a * Z_ATOM, &tmap_x, full_bar(s), (int)(d0 + 32 * a), kb * Z_BK, 0);
-          if (++s == Z_STAGES) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == Z_STAGES) { s = 0; ph ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(/*tf32*/ 2, /*A K-major*/ 0, /*B MN-major*/ 1, Z_BM, Z_BN);
-      int s = 0; uint32_t ph = 0; int it_tile = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
-        const int acc = it_tile & 1;
-        const uint32_t acc_ph = (it_tile >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+    const uint32_t idesc = make_idesc(/*tf32*/ 2, /*A K-major*/ 0, /*B MN-major*/ 1, Z_BM, Z_BN);
+    const uint32_t ahi = smem_desc_hi(1024), bhi = smem_desc_hi(512, /*SWIZZLE_128B_BASE32B*/ 1);
+    int s = 0; uint32_t ph = 0; int it_tile = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
+      const int acc = it_tile & 1;
+      const uint32_t acc_ph = (it_tile >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * Z_STAGE_BYTES, sb = sa + Z_A_BYTES;
+        if (elect_one_sync()) {
+          const uint32_t alo = smem_desc_lo(smem_base + s * Z_STAGE_BYTES, 16);
+          const uint32_t blo = smem_desc_lo(smem_base + s * Z_STAGE_BYTES + Z_A_BYTES, Z_ATOM);
 #pragma unroll
-          for (int k = 0; k < Z_BK / 8; ++k) {
+          for (int k = 0; k < Z_BK / 8; ++k)
             // A: 8 fp32 (32 B) further along the swizzled row; B: next 8 K-rows (two 4-row swizzle groups, 1024 B)
-            umma_tf32(d_tmem, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 1024, Z_ATOM, 512, /*SWIZZLE_128B_BASE32B*/ 1), idesc,
-                      (kb | k) != 0);
-          }
+            umma_tf32(d_tmem, desc64(alo + 2 * k, ahi), desc64(blo + k * (1024 >> 4), bhi), idesc, (kb | k) != 0);
           umma_commit(empty_bar(s));
-          if (++s == Z_STAGES) { s = 0; ph ^= 1; }
+          if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
         }
-        umma_commit(tfull_bar(acc));
+        __syncwarp();
+        if (++s == Z_STAGES) { s = 0; ph ^= 1; }
       }
     }
-    __syncwarp();
   } else {
     const int ew = warp - 2, quad = warp & 3, hsel = ew >> 2;
     const int row = quad * 32 + lane;

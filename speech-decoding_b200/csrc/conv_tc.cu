@@ -192,63 +192,61 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int k_iters = p.taps * p.k_blocks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t stage_tx = A_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
-        const int b = m_idx / p.m_tiles_per_sample;
-        const int t0 = (m_idx % p.m_tiles_per_sample) * BLOCK_M;
-        const int g = p.widx ? __ldg(p.widx + b) : 0;
-        const int row0 = glu ? n_idx * half_n : n_idx * p.block_n;
-        const int row1 = glu ? p.D2 + n_idx * half_n : row0 + half_n;
-        for (int j = 0; j < p.taps; ++j) {
-          const int shift = (j - (p.taps - 1) / 2) * p.dil;
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
-            mbar_wait(empty_bar(s), ph ^ 1);
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t stage_tx = A_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
+      const int b = m_idx / p.m_tiles_per_sample;
+      const int t0 = (m_idx % p.m_tiles_per_sample) * BLOCK_M;
+      const int g = p.widx ? __ldg(p.widx + b) : 0;
+      const int row0 = glu ? n_idx * half_n : n_idx * p.block_n;
+      const int row1 = glu ? p.D2 + n_idx * half_n : row0 + half_n;
+      for (int j = 0; j < p.taps; ++j) {
+        const int shift = (j - (p.taps - 1) / 2) * p.dil;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (elect_one_sync()) {
             const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + A_BYTES;
             mbar_arrive_expect_tx(full_bar(s), stage_tx);
             tma_load_3d(sa, &tmap_a, full_bar(s), kb * BLOCK_K, t0 + shift, b);
             tma_load_3d(sb, &tmap_w, full_bar(s), kb * BLOCK_K, row0, g * p.taps + j);
             tma_load_3d(sb + half_n * (BLOCK_K * 2), &tmap_w, full_bar(s), kb * BLOCK_K, row1, g * p.taps + j);
-            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, BLOCK_M, (uint32_t)p.block_n);
-      int s = 0;
-      uint32_t ph = 0;
-      int it_tile = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
-        const int acc = it_tile & 1;
-        const uint32_t acc_ph = (it_tile >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * MAX_BLOCK_N;
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16(d_tmem, ad, bd, idesc, (it | k) != 0);
-          }
-          umma_commit(empty_bar(s));
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull_bar(acc));
       }
     }
-    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    const uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, BLOCK_M, (uint32_t)p.block_n);
+    const uint32_t dhi = smem_desc_hi(1024);
+    int s = 0;
+    uint32_t ph = 0;
+    int it_tile = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
+      const int acc = it_tile & 1;
+      const uint32_t acc_ph = (it_tile >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * MAX_BLOCK_N;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t alo = smem_desc_lo(smem_base + s * p.stage_bytes, 16), blo = alo + (A_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)   // +32 B per 16-element k-step inside the swizzled row
+            umma_f16(d_tmem, desc64(alo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
+          umma_commit(empty_bar(s));
+          if (it == k_iters - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;

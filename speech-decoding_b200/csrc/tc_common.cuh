@@ -66,6 +66,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp.  The producer / MMA loops are executed by the whole warp with
+// warp-uniform control flow and only the issuing instruction is predicated on this: addresses and
+// descriptors then stay in uniform registers (no per-lane "waterfall" loops around UTMALDG / UTCHMMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- device: TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -152,6 +165,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)layout_type << 61;
   return d;
 }
+
+// constant upper half of a descriptor and the per-address lower half (so the hot loop is one 32-bit add)
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type = 2) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate:
 //   [4,6) c_format (1 = F32) | [7,10) a_format | [10,13) b_format (0 F16, 1 BF16, 2 TF32)

@@ -99,56 +99,53 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t stage_tx = (uint32_t)(2 + p.c_atoms) * ATOM_BYTES;
-      for (int pos = s_begin; pos < s_end; ++pos) {
-        const int b = p.sample_order ? __ldg(p.sample_order + pos) : pos;
-        for (int tb = 0; tb < t_blocks; ++tb) {
-          mbar_wait(empty_bar(s), ph ^ 1);
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t stage_tx = (uint32_t)(2 + p.c_atoms) * ATOM_BYTES;
+    for (int pos = s_begin; pos < s_end; ++pos) {
+      const int b = p.sample_order ? __ldg(p.sample_order + pos) : pos;
+      for (int tb = 0; tb < t_blocks; ++tb) {
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (elect_one_sync()) {
           const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + 2 * ATOM_BYTES;
           mbar_arrive_expect_tx(full_bar(s), stage_tx);
           tma_load_3d(sa, &tmap_dy, full_bar(s), n0, tb * BLOCK_T, b);
           tma_load_3d(sa + ATOM_BYTES, &tmap_dy, full_bar(s), n0 + 64, tb * BLOCK_T, b);
           for (int a = 0; a < p.c_atoms; ++a)
             tma_load_3d(sb + a * ATOM_BYTES, &tmap_x, full_bar(s), c0 + 64 * a, tb * BLOCK_T + shift, b);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(/*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1, BLOCK_MN, (uint32_t)p.block_c);
-      const uint32_t idesc_b = make_idesc(1, 1, 1, BLOCK_MN, 16);
-      int s = 0;
-      uint32_t ph = 0;
-      const int iters = (s_end - s_begin) * t_blocks;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + 2 * ATOM_BYTES;
-#pragma unroll
-        for (int k = 0; k < BLOCK_T / 16; ++k) {
-          // 16 time rows = 2048 B inside each 64-channel atom; atoms are ATOM_BYTES apart (LBO);
-          // consecutive 8-row groups are 1024 B apart (SBO)
-          const uint64_t ad = make_smem_desc(sa + k * 2048, ATOM_BYTES, 1024);
-          const uint64_t bd = make_smem_desc(sb + k * 2048, ATOM_BYTES, 1024);
-          umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0);
-          if (do_bias) {
-            const uint64_t od = make_smem_desc(ones_base, ATOM_BYTES, 1024);
-            umma_f16(tmem_base + BIAS_COL, ad, od, idesc_b, (it | k) != 0);
-          }
-        }
-        umma_commit(empty_bar(s));
+        __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      umma_commit(tfull_bar);
     }
-    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    const uint32_t idesc = make_idesc(/*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1, BLOCK_MN, (uint32_t)p.block_c);
+    const uint32_t idesc_b = make_idesc(1, 1, 1, BLOCK_MN, 16);
+    const uint32_t dhi = smem_desc_hi(1024);
+    const uint32_t olo = smem_desc_lo(ones_base, ATOM_BYTES);
+    int s = 0;
+    uint32_t ph = 0;
+    const int iters = (s_end - s_begin) * t_blocks;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        // 16 time rows = 2048 B inside each 64-channel atom; atoms are ATOM_BYTES apart (LBO);
+        // consecutive 8-row groups are 1024 B apart (SBO)
+        const uint32_t alo = smem_desc_lo(smem_base + s * p.stage_bytes, ATOM_BYTES), blo = alo + ((2 * ATOM_BYTES) >> 4);
+#pragma unroll
+        for (int k = 0; k < BLOCK_T / 16; ++k) {
+          umma_f16(tmem_base, desc64(alo + k * (2048 >> 4), dhi), desc64(blo + k * (2048 >> 4), dhi), idesc, (it | k) != 0);
+          if (do_bias) umma_f16(tmem_base + BIAS_COL, desc64(alo + k * (2048 >> 4), dhi), desc64(olo, dhi), idesc_b, (it | k) != 0);
+        }
+        umma_commit(empty_bar(s));
+        if (it == iters - 1) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
   } else {
     // ===================== epilogue: fp32 tile -> red.add into dw =====================
     const int ew = warp - 2, quad = warp & 3, hsel = ew >> 2;
