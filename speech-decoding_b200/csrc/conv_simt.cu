@@ -83,7 +83,7 @@ conv_fwd_simt_kernel(sd_conv_args a, int tiles_per_sample) {
         v = 0.f;
       }
       if (pre) pre[row + n] = from_f<T>(v);
-      if (a.act == SD_ACT_GELU) v = (n < a.N) ? gelu_f(v) : 0.f;
+      if (a.act == SD_ACT_GELU) v = (n < a.N) ? gelu_t<T>(v) : 0.f;
       if (a.out_mode == SD_OUT_BTC) {
         reinterpret_cast<T*>(a.out)[row + n] = from_f<T>(v);
       } else if (n < a.N) {

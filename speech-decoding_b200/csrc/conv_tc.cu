@@ -50,7 +50,7 @@ struct FwdParams {
   int block_n, n_tiles, m_tiles_per_sample, num_tiles, k_blocks;
   int act, out_mode, D2, Op;
   // shared-memory plan (byte offsets from the 1024-aligned base)
-  int stages, stage_bytes, pitch, off_stg0, off_stg1, off_bias, off_stats, off_bar, cols_alloc;
+  int stages, stage_bytes, pitch, pitch1, off_stg0, off_stg1, off_bias, off_stats, off_bar, cols_alloc;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -256,7 +256,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t s_bias = smem_base + p.off_bias;
     float* s_stats = reinterpret_cast<float*>(smem_gen + p.off_stats);
     const uint32_t stg0 = smem_base + p.off_stg0 + row * p.pitch;
-    const uint32_t stg1 = smem_base + p.off_stg1 + row * p.pitch;
+    const uint32_t stg1 = smem_base + p.off_stg1 + row * p.pitch1;
     // chunk range [ch0, ch1) of 16-column chunks owned by this thread
     const int nch = glu ? (half_n >> 4) : (p.block_n >> 4);
     const int ch0 = hsel ? (nch + 1) / 2 : 0;
@@ -313,7 +313,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (p.act == SD_ACT_GELU) {
             if (p.preact) sts16_bf16(stg0 + cc * 2, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = gelu_f(v[i]);
+            for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);   // bf16 mode
             if (p.out_mode == SD_OUT_BTC) sts16_bf16(stg1 + cc * 2, v);
           } else {
             sts16_bf16(stg0 + cc * 2, v);
@@ -530,15 +530,17 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   p.stage_bytes = A_BYTES + p.block_n * BLOCK_K * 2;
   p.pitch = p.block_n * 2 + 16;
   const bool need_stg1 = glu || (a.act == SD_ACT_GELU && a.out_mode == SD_OUT_BTC);
+  p.pitch1 = glu ? p.block_n + 16 : p.pitch;          // GLU output is half as wide as the accumulator tile
   const int stg_bytes = BLOCK_M * p.pitch;
-  const int tail = stg_bytes * (need_stg1 ? 2 : 1) + (glu ? 2 : 1) * p.cols_alloc * 4 + 2 * p.cols_alloc * 4 + 512;
+  const int stg1_bytes = need_stg1 ? BLOCK_M * p.pitch1 : 0;
+  const int tail = stg_bytes + stg1_bytes + (glu ? 2 : 1) * p.cols_alloc * 4 + 2 * p.cols_alloc * 4 + 512;
   int stages = (SMEM_LIMIT - 1024 - tail) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   SD_REQUIRE(stages >= 2, "conv_fwd_tc: not enough shared memory for block_n=%d", p.block_n);
   p.stages = stages;
   int off = stages * p.stage_bytes;
   p.off_stg0 = off; off += stg_bytes;
-  p.off_stg1 = off; if (need_stg1) off += stg_bytes;
+  p.off_stg1 = off; off += stg1_bytes;
   p.off_bias = off; off += (glu ? 2 : 1) * p.cols_alloc * 4;
   p.off_stats = off; off += 2 * p.cols_alloc * 4;
   off = (off + 15) / 16 * 16;

@@ -68,7 +68,7 @@ __global__ void gelu_bwd_nct_kernel(const float* __restrict__ dz, const T* __res
     int t = t0 + ty + i, c = c0 + tx;
     if (t < Tn && c < Np) {
       size_t o = base + (size_t)t * Np + c;
-      float g = (c < N) ? tile[tx][ty + i] * gelu_grad_f(to_f<T>(p[o])) : 0.f;
+      float g = (c < N) ? tile[tx][ty + i] * gelu_grad_t<T>(to_f<T>(p[o])) : 0.f;
       dp[o] = from_f<T>(g);
     }
   }
@@ -157,47 +157,50 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
 }
 __device__ __forceinline__ F8 ldp8(const float* p) { return ld8<float>(p); }
 
-constexpr int ROWS_PER_BLOCK = 128;   // rows of the slab one block walks
+constexpr int RED_ROWS = 128;   // rows per block, reduction kernels (fewer blocks => fewer atomics)
+constexpr int EW_ROWS = 64;     // rows per block, pure elementwise channel kernels
 
 // MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce (g written in place over x)
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3)
 colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ ss, double* __restrict__ out,
                  int64_t rows, int Cp) {
   extern __shared__ float red_smem[];   // [blockDim.y][Cp] x 2
   const int cv = threadIdx.x, c = cv * 8, ry = threadIdx.y, R = blockDim.y;
-  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
-  const int64_t r1 = min(rows, r0 + ROWS_PER_BLOCK);
+  constexpr int UNR = MODE == 0 ? 2 : 1;   // rows in flight per thread (register budget)
+  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS;
+  const int64_t r1 = min(rows, r0 + RED_ROWS);
   F8 a, q;
 #pragma unroll
   for (int i = 0; i < 8; ++i) a.v[i] = q.v[i] = 0.f;
   F8 sc, sh, mu, is;
   if (MODE == 1) { sc = ldp8(ss + c); sh = ldp8(ss + Cp + c); mu = ldp8(ss + 2 * Cp + c); is = ldp8(ss + 3 * Cp + c); }
-  for (int64_t r = r0 + ry; r < r1; r += 2 * R) {
-    const bool two = r + R < r1;
-    F8 v0 = ld8<T>(x + r * Cp + c), v1, y0, y1;
-    if (two) v1 = ld8<T>(x + (r + R) * Cp + c);
-    if (MODE == 1) {
-      y0 = ld8<T>(y + r * Cp + c);
-      if (two) y1 = ld8<T>(y + (r + R) * Cp + c);
+  for (int64_t r = r0 + ry; r < r1; r += UNR * R) {
+    F8 v[UNR], yy[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * R;
+      if (rr < r1) {
+        v[u] = ld8<T>(x + rr * Cp + c);
+        if (MODE == 1) yy[u] = ld8<T>(y + rr * Cp + c);
+      }
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h == 1 && !two) break;
-      F8& v = h ? v1 : v0;
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * R;
+      if (rr >= r1) break;
       if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a.v[i] += v.v[i]; q.v[i] += v.v[i] * v.v[i]; }
+        for (int i = 0; i < 8; ++i) { a.v[i] += v[u].v[i]; q.v[i] += v[u].v[i] * v[u].v[i]; }
       } else {
-        const F8& yy = h ? y1 : y0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float g = v.v[i] * gelu_grad_f(yy.v[i] * sc.v[i] + sh.v[i]);
-          v.v[i] = g;
+          float g = v[u].v[i] * gelu_grad_t<T>(fmaf(yy[u].v[i], sc.v[i], sh.v[i]));
+          v[u].v[i] = g;
           a.v[i] += g;
-          q.v[i] += g * (yy.v[i] - mu.v[i]) * is.v[i];
+          q.v[i] += g * (yy[u].v[i] - mu.v[i]) * is.v[i];
         }
-        st8<T>(x + (r + (h ? R : 0)) * Cp + c, v);
+        st8<T>(x + rr * Cp + c, v[u]);
       }
     }
   }
@@ -249,34 +252,39 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, int 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
-bn_gelu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss, T* __restrict__ u, int64_t rows, int Cp) {
+__global__ void __launch_bounds__(256, 4)
+bn_gelu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss, T* __restrict__ u_out, int64_t rows, int Cp) {
+  constexpr int UNR = 2;
   const int c = threadIdx.x * 8, ry = threadIdx.y, R = blockDim.y;
-  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK, r1 = min(rows, r0 + ROWS_PER_BLOCK);
+  const int64_t r0 = (int64_t)blockIdx.x * EW_ROWS, r1 = min(rows, r0 + EW_ROWS);
   const F8 sc = ldp8(ss + c), sh = ldp8(ss + Cp + c);
-  for (int64_t r = r0 + ry; r < r1; r += 2 * R) {
-    const bool two = r + R < r1;
-    F8 v0 = ld8<T>(y + r * Cp + c), v1;
-    if (two) v1 = ld8<T>(y + (r + R) * Cp + c);
+  for (int64_t r = r0 + ry; r < r1; r += UNR * R) {
+    F8 v[UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v0.v[i] = gelu_f(v0.v[i] * sc.v[i] + sh.v[i]);
-    st8<T>(u + r * Cp + c, v0);
-    if (two) {
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * R;
+      if (rr < r1) v[u] = ld8<T>(y + rr * Cp + c);
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v1.v[i] = gelu_f(v1.v[i] * sc.v[i] + sh.v[i]);
-      st8<T>(u + (r + R) * Cp + c, v1);
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * R;
+      if (rr >= r1) break;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u].v[i] = gelu_t<T>(fmaf(v[u].v[i], sc.v[i], sh.v[i]));
+      st8<T>(u_out + rr * Cp + c, v[u]);
     }
   }
 }
 
 // dy = scale * (g - sum_g/n - xhat * sum_gx/n)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ ss,
                     const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     int64_t rows, int64_t n_stat, int C, int Cp, int training) {
+  constexpr int UNR = 1;
   const int c = threadIdx.x * 8, ry = threadIdx.y, R = blockDim.y;
-  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK, r1 = min(rows, r0 + ROWS_PER_BLOCK);
+  const int64_t r0 = (int64_t)blockIdx.x * EW_ROWS, r1 = min(rows, r0 + EW_ROWS);
   if (blockIdx.x == 0) {
     const int tid = ry * blockDim.x + threadIdx.x;
     for (int ch = tid; ch < C; ch += blockDim.x * R) {
@@ -286,28 +294,32 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
   }
   const F8 sc = ldp8(ss + c), mu = ldp8(ss + 2 * Cp + c), is = ldp8(ss + 3 * Cp + c);
   const float invn = 1.0f / (float)n_stat;
-  F8 sg, sx;
+  // dy = k1*g + k2*y + k3 with per-channel constants
+  F8 k2, k3;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sg.v[i] = (float)red[c + i] * invn; sx.v[i] = (float)red[Cp + c + i] * invn; }
-  for (int64_t r = r0 + ry; r < r1; r += 2 * R) {
-    const bool two = r + R < r1;
-    F8 v0 = ld8<T>(g + r * Cp + c), v1, y0, y1;
-    if (two) v1 = ld8<T>(g + (r + R) * Cp + c);
-    if (training) {
-      y0 = ld8<T>(y + r * Cp + c);
-      if (two) y1 = ld8<T>(y + (r + R) * Cp + c);
-    }
+  for (int i = 0; i < 8; ++i) {
+    const float sg = (float)red[c + i] * invn, sx = (float)red[Cp + c + i] * invn;
+    k2.v[i] = training ? -sc.v[i] * is.v[i] * sx : 0.f;
+    k3.v[i] = training ? sc.v[i] * (mu.v[i] * is.v[i] * sx - sg) : 0.f;
+  }
+  for (int64_t r = r0 + ry; r < r1; r += UNR * R) {
+    F8 v[UNR], yy[UNR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v0.v[i] = training ? sc.v[i] * (v0.v[i] - sg.v[i] - (y0.v[i] - mu.v[i]) * is.v[i] * sx.v[i]) : sc.v[i] * v0.v[i];
-    }
-    st8<T>(g + r * Cp + c, v0);
-    if (two) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v1.v[i] = training ? sc.v[i] * (v1.v[i] - sg.v[i] - (y1.v[i] - mu.v[i]) * is.v[i] * sx.v[i]) : sc.v[i] * v1.v[i];
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * R;
+      if (rr < r1) {
+        v[u] = ld8<T>(g + rr * Cp + c);
+        if (training) yy[u] = ld8<T>(y + rr * Cp + c);
       }
-      st8<T>(g + (r + R) * Cp + c, v1);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t rr = r + (int64_t)u * R;
+      if (rr >= r1) break;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        v[u].v[i] = training ? fmaf(sc.v[i], v[u].v[i], fmaf(k2.v[i], yy[u].v[i], k3.v[i])) : sc.v[i] * v[u].v[i];
+      st8<T>(g + rr * Cp + c, v[u]);
     }
   }
 }
@@ -393,7 +405,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(T* __restrict__ du, const
   for (; i < n8; i += step) {
     F8 v = ld8<T>(du + i * 8), q = ld8<T>(p + i * 8);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v.v[k] *= gelu_grad_f(q.v[k]);
+    for (int k = 0; k < 8; ++k) v.v[k] *= gelu_grad_t<T>(q.v[k]);
     st8<T>(du + i * 8, v);
   }
 }
@@ -458,7 +470,7 @@ int sd_colstats(const void* x, double* stats, int64_t rows, int Cp, int dtype, v
   SD_REQUIRE(Cp <= 2048, "sd_colstats: Cp too large");
   dim3 block(Cp / 8, chan_block_rows(Cp));
   const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
-  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 0><<<cdiv(rows, ROWS_PER_BLOCK), block, smem, (cudaStream_t)stream>>>((T*)x, nullptr, nullptr, stats, rows, Cp));
+  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 0><<<cdiv(rows, RED_ROWS), block, smem, (cudaStream_t)stream>>>((T*)x, nullptr, nullptr, stats, rows, Cp));
   return check_launch("colstats");
 }
 
@@ -474,7 +486,7 @@ int sd_bn_finalize(const double* stats, int C, int Cp, int64_t n, const float* g
 int sd_bn_gelu_fwd(const void* y, const float* ss, void* u, int64_t rows, int Cp, int dtype, void* stream) {
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_gelu_fwd: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
-  DISPATCH_DTYPE(dtype, bn_gelu_fwd_kernel<T><<<cdiv(rows, ROWS_PER_BLOCK), block, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)u, rows, Cp));
+  DISPATCH_DTYPE(dtype, bn_gelu_fwd_kernel<T><<<cdiv(rows, EW_ROWS), block, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)u, rows, Cp));
   return check_launch("bn_gelu_fwd");
 }
 
@@ -483,7 +495,7 @@ int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* re
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_gelu_bwd_reduce: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
   const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
-  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1><<<cdiv(rows, ROWS_PER_BLOCK), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
+  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1><<<cdiv(rows, RED_ROWS), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
   return check_launch("bn_gelu_bwd_reduce");
 }
 
@@ -491,7 +503,7 @@ int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* re
                     int64_t rows, int64_t n_stat, int C, int Cp, int training, int dtype, void* stream) {
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_bwd_apply: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<cdiv(rows, ROWS_PER_BLOCK), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, C, Cp, training));
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<cdiv(rows, EW_ROWS), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, C, Cp, training));
   return check_launch("bn_bwd_apply");
 }
 

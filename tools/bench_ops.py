@@ -65,6 +65,20 @@ def main():
     ss = torch.randn(4, 320, device=DEV)
     ms = timeit(lambda: ops.bn_gelu_fwd(y, ss, u))
     print("bn_gelu_fwd %.3f ms  %.0f GB/s" % (ms, 2 * y.numel() * 2 / ms / 1e6))
+    ms = timeit(lambda: torch.nn.functional.gelu(y, out=u) if False else u.copy_(y)); print("torch copy_ same shape %.3f ms %.0f GB/s" % (ms, 2 * y.numel() * 2 / ms / 1e6))
+    ms = timeit(lambda: torch.nn.functional.gelu(y)); print("torch gelu same shape %.3f ms %.0f GB/s" % (ms, 2 * y.numel() * 2 / ms / 1e6))
+    yb = torch.randn(4 * B, T, 320, device=DEV).to(dt); ub = torch.empty_like(yb)
+    def many(fn, n=10):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n): fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    ms = many(lambda: ops.bn_gelu_fwd(yb, ss, ub)); print("bn_gelu_fwd 4x rows, back-to-back %.3f ms %.0f GB/s" % (ms, 2 * yb.numel() * 2 / ms / 1e6))
+    ms = many(lambda: ub.copy_(yb)); print("torch copy_ 4x rows, back-to-back %.3f ms %.0f GB/s" % (ms, 2 * yb.numel() * 2 / ms / 1e6))
+    du = torch.randn_like(yb); red = torch.zeros(2, 320, dtype=torch.float64, device=DEV); dg = torch.zeros(320, device=DEV); db = torch.zeros(320, device=DEV)
+    ms = many(lambda: ops.bn_gelu_bwd(du, yb, ss, red, dg, db, 320, True)); print("bn_gelu_bwd (reduce+apply) 4x rows %.3f ms %.0f GB/s" % (ms, 5 * yb.numel() * 2 / ms / 1e6))
     Y = torch.randn(B, 1024 * T, device=DEV)
     Z = torch.randn(B, 1024 * T, device=DEV)
     ms = timeit(lambda: ops.rownorm2(Y)); print("rownorm2 %.3f ms %.0f GB/s" % (ms, Y.numel() * 4 / ms / 1e6))
