@@ -139,10 +139,12 @@ int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* re
                           int dtype, void* stream);
 /* dy = scale*(g - sum_g/n - xhat*sum_gx/n) in place over g; also dgamma = sum_gx, dbeta = sum_g (C).
  * n = n_stat = number of rows the statistics cover (rows * world size under SyncBN).
+ * dgamma/dbeta are written as red * dparam_scale (1/world under SyncBN, where red is already the global sum
+ * and the parameter gradients are summed across ranks once more afterwards).
  * eval-mode BN (training=0): dy = scale*g. */
 int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* red, float* dgamma,
-                    float* dbeta, int64_t rows, int64_t n_stat, int C, int Cp, int training, int dtype,
-                    void* stream);
+                    float* dbeta, int64_t rows, int64_t n_stat, float dparam_scale, int C, int Cp, int training,
+                    int dtype, void* stream);
 
 /* ---- GLU (models.py:164) and GELU backward ------------------------------------------------------- */
 int sd_glu_fwd(const void* y2, void* out, int64_t rows, int D2, int Np, int Op, int dtype, void* stream);

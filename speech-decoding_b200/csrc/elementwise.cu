@@ -281,15 +281,15 @@ template <typename T>
 __global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ ss,
                     const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                    int64_t rows, int64_t n_stat, int C, int Cp, int training) {
+                    int64_t rows, int64_t n_stat, float dscale, int C, int Cp, int training) {
   constexpr int UNR = 1;
   const int c = threadIdx.x * 8, ry = threadIdx.y, R = blockDim.y;
   const int64_t r0 = (int64_t)blockIdx.x * EW_ROWS, r1 = min(rows, r0 + EW_ROWS);
   if (blockIdx.x == 0) {
     const int tid = ry * blockDim.x + threadIdx.x;
     for (int ch = tid; ch < C; ch += blockDim.x * R) {
-      if (dbeta) dbeta[ch] = (float)red[ch];
-      if (dgamma) dgamma[ch] = (float)red[Cp + ch];
+      if (dbeta) dbeta[ch] = (float)red[ch] * dscale;
+      if (dgamma) dgamma[ch] = (float)red[Cp + ch] * dscale;
     }
   }
   const F8 sc = ldp8(ss + c), mu = ldp8(ss + 2 * Cp + c), is = ldp8(ss + 3 * Cp + c);
@@ -500,10 +500,10 @@ int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* re
 }
 
 int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* red, float* dgamma, float* dbeta,
-                    int64_t rows, int64_t n_stat, int C, int Cp, int training, int dtype, void* stream) {
+                    int64_t rows, int64_t n_stat, float dparam_scale, int C, int Cp, int training, int dtype, void* stream) {
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_bwd_apply: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<cdiv(rows, EW_ROWS), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, C, Cp, training));
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<cdiv(rows, EW_ROWS), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, dparam_scale, C, Cp, training));
   return check_launch("bn_bwd_apply");
 }
 

@@ -113,13 +113,14 @@ def bn_gelu_bwd(du, y, ss, red, dgamma, dbeta, C, training, group=None):
     """in place: du -> dy (gradient w.r.t. the pre-BN tensor y).  With `group`
     (SyncBN) the two per-channel sums are all-reduced between the passes."""
     rows, Cp = y.shape[0] * y.shape[1], y.shape[2]
-    n_stat = rows
+    n_stat, dscale = rows, 1.0
     nat.call("sd_bn_gelu_bwd_reduce", _p(du), _p(y), _p(ss), _p(red), rows, Cp, code_of(y), _st())
     if group is not None and training:
         import torch.distributed as dist
         dist.all_reduce(red, group=group)
         n_stat = rows * dist.get_world_size(group)
-    nat.call("sd_bn_bwd_apply", _p(du), _p(y), _p(ss), _p(red), _p(dgamma), _p(dbeta), rows, n_stat, C, Cp,
+        dscale = 1.0 / dist.get_world_size(group)     # red is global already; the grad all-reduce sums once more
+    nat.call("sd_bn_bwd_apply", _p(du), _p(y), _p(ss), _p(red), _p(dgamma), _p(dbeta), rows, n_stat, dscale, C, Cp,
              int(training), code_of(y), _st())
 
 
