@@ -13,10 +13,11 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM
 // allocator, warps 2..9 = epilogue: two warps per TMEM lane quadrant, each thread owns one output row
 // and half of the tile's columns.  smem ring of TMA stages; accumulators double-buffered in TMEM so
-// the epilogue of tile i overlaps the MMAs of tile i+1.  Epilogue I/O goes through a per-row smem
-// staging line and 1-D bulk copies (cp.async.bulk): the residual row segment is prefetched into the
-// staging line while the MMAs run, the finished row segment leaves as one contiguous bulk store, so
-// global traffic is full-sector both ways and no cross-thread synchronisation is needed.
+// the epilogue of tile i overlaps the MMAs of tile i+1.  Epilogue I/O goes through a per-warp smem
+// staging tile (32 rows x the warp's column segment) moved by TMA tensor copies: the residual tile is
+// prefetched while the MMAs run and the finished tile leaves as one tensor store per warp, so global
+// traffic is full-sector both ways, out-of-range rows/columns are clipped by the TMA unit, and the only
+// synchronisation is a __syncwarp.
 // Persistent grid: one CTA per SM looping over tiles, n-tiles of the same rows adjacent in time so
 // the activation slab is re-read from L2, not HBM.
 #include "tc_common.cuh"
@@ -50,7 +51,12 @@ struct FwdParams {
   int block_n, n_tiles, m_tiles_per_sample, num_tiles, k_blocks;
   int act, out_mode, D2, Op;
   // shared-memory plan (byte offsets from the 1024-aligned base)
-  int stages, stage_bytes, pitch, pitch1, off_stg0, off_stg1, off_bias, off_stats, off_bar, cols_alloc;
+  int stages, stage_bytes, w0cols, off_stg0, off_stg1, off_bias, off_stats, off_bar, cols_alloc;
+};
+
+// tensor maps of the epilogue tensors, one per column-half of the tile (the halves may differ in width)
+struct EpiMaps {
+  CUtensorMap out[2], pre[2], res[2], preb[2];   // preb: gate half of the GLU pre-activation
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -136,7 +142,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                   const FwdParams p) {
+                   const __grid_constant__ EpiMaps em, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
@@ -164,7 +170,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), NUM_EPI_WARPS);
     }
-    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 32);
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
     fence_barrier_init();
   }
   // bias (zero beyond N) and statistics accumulators in shared memory
@@ -255,13 +261,25 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int row = quad * 32 + lane;
     const uint32_t s_bias = smem_base + p.off_bias;
     float* s_stats = reinterpret_cast<float*>(smem_gen + p.off_stats);
-    const uint32_t stg0 = smem_base + p.off_stg0 + row * p.pitch;
-    const uint32_t stg1 = smem_base + p.off_stg1 + row * p.pitch1;
-    // chunk range [ch0, ch1) of 16-column chunks owned by this thread
+    // chunk range [ch0, ch1) of 16-column chunks owned by this warp
     const int nch = glu ? (half_n >> 4) : (p.block_n >> 4);
     const int ch0 = hsel ? (nch + 1) / 2 : 0;
     const int ch1 = hsel ? nch : (nch + 1) / 2;
     const int seg_col = ch0 * 16, seg_cols = (ch1 - ch0) * 16;
+    const uint32_t seg_bytes = (uint32_t)seg_cols * 2;          // one staged row of this warp's segment
+    const uint32_t box_bytes = 32u * seg_bytes;
+    // staging tiles ([32 rows][seg_cols] bf16, dense) of this warp
+    //   non-GLU: stg0 = conv output / pre-activation, stg1 = activated output (GELU with BTC output)
+    //   GLU:     stg0 = value half then gate half of the pre-activation, stg1 = gated output
+    const uint32_t quad0 = smem_base + p.off_stg0 + quad * (32 * p.block_n * 2);
+    const uint32_t stg0 = quad0 + (glu ? 2 : 1) * (hsel ? 32 * p.w0cols * 2 : 0);
+    const uint32_t stg0b = stg0 + box_bytes;                                     // GLU gate half
+    const uint32_t stg1 = smem_base + p.off_stg1 + quad * (32 * (glu ? half_n : p.block_n) * 2) + (hsel ? 32 * p.w0cols * 2 : 0);
+    const uint32_t my0 = stg0 + lane * seg_bytes, my0b = stg0b + lane * seg_bytes, my1 = stg1 + lane * seg_bytes;
+    const CUtensorMap* m_out = &em.out[hsel];
+    const CUtensorMap* m_pre = &em.pre[hsel];
+    const CUtensorMap* m_res = &em.res[hsel];
+    const CUtensorMap* m_preb = &em.preb[hsel];
     uint32_t res_ph = 0;
 
     int it_tile = 0;
@@ -270,24 +288,25 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t acc_ph = (it_tile >> 1) & 1;
       const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
       const int b = m_idx / p.m_tiles_per_sample;
-      const int t = (m_idx % p.m_tiles_per_sample) * BLOCK_M + row;
+      const int t_w = (m_idx % p.m_tiles_per_sample) * BLOCK_M + quad * 32;   // first row of this warp
+      const int t = t_w + lane;
       const bool valid = t < p.T;
-      const size_t grow = (size_t)b * p.T + (valid ? t : 0);
       const int n0 = glu ? n_idx * half_n : n_idx * p.block_n;  // first output channel of the tile
       const int lim = glu ? p.Op : p.Np;
-      // number of this thread's columns that exist in global memory (multiple of 8)
-      int gcols = lim - (n0 + seg_col);
-      gcols = gcols < 0 ? 0 : (gcols > seg_cols ? seg_cols : gcols);
+      // does this warp's tile intersect the tensor at all?  (TMA clips partial overlap)
+      const bool live = seg_cols > 0 && t_w < p.T && n0 + seg_col < lim;
 
-      // previous tile's bulk stores must have finished reading this thread's staging lines
-      bulk_wait_read0();
+      // the previous tile's tensor stores must have finished reading the staging tiles
+      if (elect_one_sync()) bulk_wait_read0();
+      __syncwarp();
       if (p.res) {
-        const uint32_t bytes = (valid && gcols > 0) ? (uint32_t)gcols * 2 : 0;
-        if (bytes) {
-          mbar_arrive_expect_tx(res_bar(ew), bytes);
-          bulk_load(stg0 + seg_col * 2, p.res + grow * p.Np + n0 + seg_col, bytes, res_bar(ew));
-        } else {
-          mbar_arrive(res_bar(ew));
+        if (elect_one_sync()) {
+          if (live) {
+            mbar_arrive_expect_tx(res_bar(ew), box_bytes);
+            tma_load_3d(stg0, m_res, res_bar(ew), n0 + seg_col, t_w, b);
+          } else {
+            mbar_arrive(res_bar(ew));
+          }
         }
       }
       mbar_wait(tfull_bar(acc), acc_ph);
@@ -302,6 +321,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (!glu) {
         for (int c = ch0; c < ch1; ++c) {
           const int cc = c * 16, nb = n0 + cc;
+          const uint32_t so = (uint32_t)(c - ch0) * 32;
           uint32_t r[16];
           tmem_ld16(taddr + cc, r);
           tmem_ld_wait();
@@ -309,14 +329,14 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
           lds16_f32_add(s_bias + nb * 4, v);
-          if (p.res && valid && nb < p.Np) lds16_bf16_add(stg0 + cc * 2, v);
+          if (p.res && live) lds16_bf16_add(my0 + so, v);
           if (p.act == SD_ACT_GELU) {
-            if (p.preact) sts16_bf16(stg0 + cc * 2, v);
+            if (p.preact) sts16_bf16(my0 + so, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);   // bf16 mode
-            if (p.out_mode == SD_OUT_BTC) sts16_bf16(stg1 + cc * 2, v);
+            if (p.out_mode == SD_OUT_BTC) sts16_bf16(my1 + so, v);
           } else {
-            sts16_bf16(stg0 + cc * 2, v);
+            sts16_bf16(my0 + so, v);
           }
           if (p.out_mode == SD_OUT_NCT_F32 && valid) {
 #pragma unroll
@@ -345,22 +365,24 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
           }
         }
-        if (valid && gcols > 0) {
-          fence_proxy_async();
-          const uint32_t bytes = (uint32_t)gcols * 2;
-          const size_t goff = grow * p.Np + n0 + seg_col;
-          if (p.act == SD_ACT_GELU) {
-            if (p.preact) bulk_store(p.preact + goff, stg0 + seg_col * 2, bytes);
-            if (p.out_mode == SD_OUT_BTC) bulk_store(p.out_btc + goff, stg1 + seg_col * 2, bytes);
-          } else {
-            bulk_store(p.out_btc + goff, stg0 + seg_col * 2, bytes);
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one_sync()) {
+          if (live) {
+            if (p.act == SD_ACT_GELU) {
+              if (p.preact) tma_store_3d(m_pre, stg0, n0 + seg_col, t_w, b);
+              if (p.out_mode == SD_OUT_BTC) tma_store_3d(m_out, stg1, n0 + seg_col, t_w, b);
+            } else {
+              tma_store_3d(m_out, stg0, n0 + seg_col, t_w, b);
+            }
           }
+          bulk_commit();
         }
-        bulk_commit();
       } else {
         // GLU: tile columns [0,half) = value channels n0.., [half, 2*half) = gate channels D2+n0..
         for (int c = ch0; c < ch1; ++c) {
           const int cc = c * 16, cb = n0 + cc;
+          const uint32_t so = (uint32_t)(c - ch0) * 32;
           uint32_t ra[16], rb[16];
           tmem_ld16(taddr + cc, ra);
           tmem_ld16(taddr + half_n + cc, rb);
@@ -374,28 +396,25 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           lds16_f32_add(s_bias + cb * 4, va);
           lds16_f32_add(s_bias + (p.cols_alloc + cb) * 4, vb);
           if (p.preact) {
-            sts16_bf16(stg0 + cc * 2, va);
-            sts16_bf16(stg0 + (half_n + cc) * 2, vb);
+            sts16_bf16(my0 + so, va);
+            sts16_bf16(my0b + so, vb);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) va[i] = (cb + i < p.D2) ? va[i] * sigmoid_f(vb[i]) : 0.f;
-          sts16_bf16(stg1 + cc * 2, va);
+          sts16_bf16(my1 + so, va);
         }
-        if (valid && gcols > 0) {
-          fence_proxy_async();
-          const uint32_t bytes = (uint32_t)gcols * 2;
-          if (p.preact) {
-            // D2 % 8 == 0 on this path, so the pre-activation segments never run past their half
-            int pc = p.D2 - (n0 + seg_col);
-            pc = pc < 0 ? 0 : (pc > seg_cols ? seg_cols : pc);
-            if (pc > 0) {
-              bulk_store(p.preact + grow * p.Np + n0 + seg_col, stg0 + seg_col * 2, (uint32_t)pc * 2);
-              bulk_store(p.preact + grow * p.Np + p.D2 + n0 + seg_col, stg0 + (half_n + seg_col) * 2, (uint32_t)pc * 2);
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one_sync()) {
+          if (live) {
+            if (p.preact && n0 + seg_col < p.D2) {   // each half is its own D2-wide tensor: clipped at D2
+              tma_store_3d(m_pre, stg0, n0 + seg_col, t_w, b);
+              tma_store_3d(m_preb, stg0b, n0 + seg_col, t_w, b);
             }
+            tma_store_3d(m_out, stg1, n0 + seg_col, t_w, b);
           }
-          bulk_store(p.out_btc + grow * p.Op + n0 + seg_col, stg1 + seg_col * 2, bytes);
+          bulk_commit();
         }
-        bulk_commit();
       }
       if (p.rownorm2) {
         sumsq = warp_sum(sumsq);
@@ -405,7 +424,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
-    bulk_wait0();
+    if (elect_one_sync()) bulk_wait0();
+    __syncwarp();
     if (p.stats) {
       epi_bar_sync();
       const int et = threadIdx.x - 64;
@@ -435,6 +455,12 @@ int pick_block_n(int n_total, int gran) {
     if (pad < best_pad) { best_pad = pad; best_bn = bn; }
   }
   return best_bn;
+}
+
+CUtensorMap ta_dummy() {
+  CUtensorMap m;
+  memset(&m, 0, sizeof(m));
+  return m;
 }
 
 int sm_count() {
@@ -528,11 +554,12 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
 
   // shared-memory plan
   p.stage_bytes = A_BYTES + p.block_n * BLOCK_K * 2;
-  p.pitch = p.block_n * 2 + 16;
+  const int nch = (glu ? p.block_n / 2 : p.block_n) / 16;
+  const int w0 = (nch + 1) / 2 * 16, w1 = nch / 2 * 16;          // column widths of the two warp halves
+  p.w0cols = w0;
   const bool need_stg1 = glu || (a.act == SD_ACT_GELU && a.out_mode == SD_OUT_BTC);
-  p.pitch1 = glu ? p.block_n + 16 : p.pitch;          // GLU output is half as wide as the accumulator tile
-  const int stg_bytes = BLOCK_M * p.pitch;
-  const int stg1_bytes = need_stg1 ? BLOCK_M * p.pitch1 : 0;
+  const int stg_bytes = BLOCK_M * p.block_n * 2;
+  const int stg1_bytes = need_stg1 ? BLOCK_M * (glu ? p.block_n / 2 : p.block_n) * 2 : 0;
   const int tail = stg_bytes + stg1_bytes + (glu ? 2 : 1) * p.cols_alloc * 4 + 2 * p.cols_alloc * 4 + 512;
   int stages = (SMEM_LIMIT - 1024 - tail) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -548,6 +575,41 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   const int smem_bytes = off + 1024;
   SD_REQUIRE(smem_bytes <= SMEM_LIMIT, "conv_fwd_tc: shared-memory plan %d exceeds limit", smem_bytes);
 
+  // tensor maps of the epilogue tensors: (cols, T, B) with a (w, 32, 1) box, no swizzle
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  const int widths[2] = {w0, w1};
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t w = (uint32_t)widths[h];
+    if (w == 0) { em.out[h] = em.out[0]; em.pre[h] = em.pre[0]; em.res[h] = em.res[0]; em.preb[h] = em.preb[0]; continue; }
+    const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle NS = CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (a.out_mode == SD_OUT_BTC) {
+      const uint64_t oc = glu ? (uint64_t)p.Op : (uint64_t)a.Np;
+      if (make_tmap_3d(&em.out[h], BF, a.out, oc, (uint64_t)a.T, (uint64_t)a.B, oc * 2, (uint64_t)a.T * oc * 2, w, 32, 1, NS)) return 1;
+    } else {
+      em.out[h] = ta_dummy();
+    }
+    if (a.preact) {
+      if (glu) {
+        const uint64_t d2 = (uint64_t)p.D2;
+        if (make_tmap_3d(&em.pre[h], BF, a.preact, d2, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, w, 32, 1, NS)) return 1;
+        if (make_tmap_3d(&em.preb[h], BF, reinterpret_cast<const __nv_bfloat16*>(a.preact) + p.D2, d2, (uint64_t)a.T, (uint64_t)a.B,
+                         (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, w, 32, 1, NS)) return 1;
+      } else {
+        if (make_tmap_3d(&em.pre[h], BF, a.preact, (uint64_t)a.Np, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, w, 32, 1, NS)) return 1;
+        em.preb[h] = em.pre[h];
+      }
+    } else {
+      em.pre[h] = ta_dummy(); em.preb[h] = ta_dummy();
+    }
+    if (a.res) {
+      if (make_tmap_3d(&em.res[h], BF, a.res, (uint64_t)a.Np, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, w, 32, 1, NS)) return 1;
+    } else {
+      em.res[h] = ta_dummy();
+    }
+  }
+
   CUtensorMap ta, tw;
   if (make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, (uint64_t)a.Kp, (uint64_t)a.T, (uint64_t)a.B,
                    (uint64_t)a.Kp * 2, (uint64_t)a.T * a.Kp * 2, BLOCK_K, BLOCK_M, 1))
@@ -562,7 +624,7 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
     attr_set = true;
   }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_fwd_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(ta, tw, p);
+  conv_fwd_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(ta, tw, em, p);
   return check_launch("conv_fwd_tc");
 }
 
