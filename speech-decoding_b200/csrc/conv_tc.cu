@@ -348,25 +348,29 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 if (nb + i < p.N) sumsq += v[i] * v[i];
             }
           }
-          if (p.stats) {  // statistics of the values as stored (bf16-rounded); invalid rows contribute 0
-            float s1[16], s2[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float q = valid ? bf16_round(v[i]) : 0.f;
-              s1[i] = q;
-              s2[i] = q * q;
-            }
-            float cs = warp_colsum16(s1, lane);
-            float cq = warp_colsum16(s2, lane);
-            if ((lane & 1) == 0) {
-              const int n = nb + col_of_lane(lane);
-              atomicAdd(s_stats + n, cs);
-              atomicAdd(s_stats + p.cols_alloc + n, cq);
-            }
-          }
         }
         fence_proxy_async();
         __syncwarp();
+        if (p.stats && live) {
+          // BatchNorm batch statistics of the values exactly as stored (bf16): column sums over this warp's
+          // staged tile -- lane = column pair, conflict-free 4-byte reads down the rows
+          const int rows_valid = min(32, p.T - t_w);
+          for (int cp = lane; cp < (seg_cols >> 1); cp += 32) {
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            for (int r = 0; r < rows_valid; ++r) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(stg0 + r * seg_bytes + cp * 4));
+              float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+              s0 += f.x; s1 += f.y;
+              q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+            }
+            const int n = n0 + seg_col + 2 * cp;
+            atomicAdd(s_stats + n, s0);
+            atomicAdd(s_stats + n + 1, s1);
+            atomicAdd(s_stats + p.cols_alloc + n, q0);
+            atomicAdd(s_stats + p.cols_alloc + n + 1, q1);
+          }
+        }
         if (elect_one_sync()) {
           if (live) {
             if (p.act == SD_ACT_GELU) {
