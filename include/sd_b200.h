@@ -121,6 +121,8 @@ typedef struct {
   int B, T, K, Kp, N, Np, taps, dil, G;
   int64_t gs, sn, sk, sj;
   int dtype;
+  void* workspace;          /* optional scratch for split-K partials (tensor-core path); NULL => atomics */
+  int64_t workspace_bytes;
 } sd_wgrad_args;
 int sd_conv_wgrad(const sd_wgrad_args* a, void* stream);
 

@@ -40,6 +40,8 @@ struct WgParams {
   int B, T, N, K, taps, dil, G;
   long long gs, sn, sk, sj;
   int block_c, c_atoms, n_tiles, c_tiles, nsplit, stage_bytes;
+  float* ws;        // split-K partials [nsplit][taps][n_tiles*128][c_tiles*block_c] (+ bias [nsplit][n_tiles*128]) or NULL
+  float* ws_bias;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -156,11 +158,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     float* dwn = p.dw + (long long)g * p.gs + (long long)n * p.sn + (long long)j * p.sj;
+    const int wcols = p.c_tiles * p.block_c, wrows = p.n_tiles * BLOCK_MN;
+    float* wsn = p.ws ? p.ws + (((size_t)split * p.taps + j) * wrows + (n0 + quad * 32 + lane)) * wcols + c0 : nullptr;
     for (int c = ch0; c < ch1; ++c) {
       uint32_t r[16];
       tmem_ld16(taddr + c * 16, r);
       tmem_ld_wait();
-      if (n < p.N) {
+      if (wsn) {      // split-K partial, summed by wgrad_reduce_kernel (no atomics on the hot tensor)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(wsn + c * 16 + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+      } else if (n < p.N) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int cc = c0 + c * 16 + i;
@@ -172,13 +180,218 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
       uint32_t r[16];
       tmem_ld16(taddr + BIAS_COL, r);
       tmem_ld_wait();
-      if (n < p.N) atomicAdd(p.dbias + n, __uint_as_float(r[0]));
+      if (p.ws_bias) p.ws_bias[(size_t)split * wrows + n0 + quad * 32 + lane] = __uint_as_float(r[0]);
+      else if (n < p.N) atomicAdd(p.dbias + n, __uint_as_float(r[0]));
     }
     tc_fence_before();
   }
 
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k=3 variant: one CTA owns all three taps of its (n-tile, c-tile).  The x tile is loaded ONCE per time
+// block with a halo of `dil` rows on each side ((64+2*dil) rows x 64 channels per atom) and the taps are
+// UMMA descriptors whose start address is offset by j*dil rows inside that tile -- SWIZZLE_128B operands
+// accept arbitrary 128-byte row offsets with base_offset 0 (profiles/r1_probe_umma_desc_row_offset.txt).
+// Operand bytes per MMA drop from 40 KB to 17 KB per tap-k-block, which is what the L2->SM ingest rate
+// (~45 B/clk/SM) needs for the tensor pipe to stay busy.  Accumulators: tap j at TMEM column j*160.
+// ------------------------------------------------------------------------------------------------------
+constexpr int W3_STAGES = 4;
+constexpr int W3_TAP_COLS = 160;
+constexpr int W3_BIAS_COL = 480;
+
+struct Wg3Params {
+  float* dw;
+  float* dbias;
+  const int* sample_order;
+  const int* group_offsets;
+  int B, T, N, K, dil, G;
+  long long gs, sn, sk, sj;
+  int block_c, c_atoms, n_tiles, c_tiles, nsplit, stage_bytes, brows, batom_bytes;
+  float* ws;
+  float* ws_bias;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                      const Wg3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t ones_base = smem_base + W3_STAGES * p.stage_bytes;
+  const uint32_t bar_base = ones_base + ONES_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (W3_STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * W3_STAGES);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * W3_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int item = blockIdx.x;
+  const int split = item % p.nsplit; item /= p.nsplit;
+  const int g = item % p.G; item /= p.G;
+  const int c_tile = item % p.c_tiles;
+  const int n_tile = item / p.c_tiles;
+  const int n0 = n_tile * BLOCK_MN, c0 = c_tile * p.block_c;
+  const int pos0 = p.group_offsets ? p.group_offsets[g] : 0;
+  const int pos1 = p.group_offsets ? p.group_offsets[g + 1] : p.B;
+  const int cnt = pos1 - pos0;
+  const int per = (cnt + p.nsplit - 1) / p.nsplit;
+  const int s_begin = pos0 + split * per;
+  const int s_end = min(pos1, s_begin + per);
+  if (s_begin >= s_end) return;
+  const bool do_bias = p.dbias != nullptr && c_tile == 0;
+  const int t_blocks = (p.T + BLOCK_T - 1) / BLOCK_T;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_dy);
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < W3_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + W3_STAGES * p.stage_bytes);
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NUM_THREADS) ones[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t stage_tx = 2u * ATOM_BYTES + (uint32_t)p.c_atoms * (uint32_t)(BLOCK_T + 2 * p.dil) * 128u;
+    for (int pos = s_begin; pos < s_end; ++pos) {
+      const int b = p.sample_order ? __ldg(p.sample_order + pos) : pos;
+      for (int tb = 0; tb < t_blocks; ++tb) {
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + 2 * ATOM_BYTES;
+          mbar_arrive_expect_tx(full_bar(s), stage_tx);
+          tma_load_3d(sa, &tmap_dy, full_bar(s), n0, tb * BLOCK_T, b);
+          tma_load_3d(sa + ATOM_BYTES, &tmap_dy, full_bar(s), n0 + 64, tb * BLOCK_T, b);
+          for (int a = 0; a < p.c_atoms; ++a)
+            tma_load_3d(sb + a * p.batom_bytes, &tmap_x, full_bar(s), c0 + 64 * a, tb * BLOCK_T - p.dil, b);
+        }
+        __syncwarp();
+        if (++s == W3_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(/*bf16*/ 1, 1, 1, BLOCK_MN, (uint32_t)p.block_c);
+    const uint32_t idesc_b = make_idesc(1, 1, 1, BLOCK_MN, 16);
+    const uint32_t dhi = smem_desc_hi(1024);
+    const uint32_t olo = smem_desc_lo(ones_base, ATOM_BYTES);
+    const uint32_t tap_step = (uint32_t)(p.dil * 128) >> 4;      // descriptor units (16 B) per tap
+    int s = 0;
+    uint32_t ph = 0;
+    const int iters = (s_end - s_begin) * t_blocks;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t alo = smem_desc_lo(smem_base + s * p.stage_bytes, ATOM_BYTES);
+        const uint32_t blo = smem_desc_lo(smem_base + s * p.stage_bytes + 2 * ATOM_BYTES, (uint32_t)p.batom_bytes);
+#pragma unroll
+        for (int k = 0; k < BLOCK_T / 16; ++k) {
+          const uint64_t ad = desc64(alo + k * (2048 >> 4), dhi);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)     // tap j reads x rows t + (j-1)*dil = halo-tile rows (j*dil + ...)
+            umma_f16(tmem_base + j * W3_TAP_COLS, ad, desc64(blo + j * tap_step + k * (2048 >> 4), dhi), idesc, (it | k) != 0);
+          if (do_bias) umma_f16(tmem_base + W3_BIAS_COL, ad, desc64(olo, dhi), idesc_b, (it | k) != 0);
+        }
+        umma_commit(empty_bar(s));
+        if (it == iters - 1) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+      if (++s == W3_STAGES) { s = 0; ph ^= 1; }
+    }
+  } else {
+    const int ew = warp - 2, quad = warp & 3, hsel = ew >> 2;
+    const int n = n0 + quad * 32 + lane;
+    const int nch = p.block_c >> 4;
+    const int ch0 = hsel ? (nch + 1) / 2 : 0, ch1 = hsel ? nch : (nch + 1) / 2;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* dwn = p.dw + (long long)g * p.gs + (long long)n * p.sn;
+    const int wcols = p.c_tiles * p.block_c, wrows = p.n_tiles * BLOCK_MN;
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      float* wsn = p.ws ? p.ws + (((size_t)split * 3 + j) * wrows + (n0 + quad * 32 + lane)) * wcols + c0 : nullptr;
+      for (int c = ch0; c < ch1; ++c) {
+        uint32_t r[16];
+        tmem_ld16(taddr + j * W3_TAP_COLS + c * 16, r);
+        tmem_ld_wait();
+        if (wsn) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(wsn + c * 16 + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        } else if (n < p.N) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int cc = c0 + c * 16 + i;
+            if (cc < p.K) atomicAdd(dwn + (long long)cc * p.sk + (long long)j * p.sj, __uint_as_float(r[i]));
+          }
+        }
+      }
+    }
+    if (do_bias && hsel == 0) {
+      uint32_t r[16];
+      tmem_ld16(taddr + W3_BIAS_COL, r);
+      tmem_ld_wait();
+      if (p.ws_bias) p.ws_bias[(size_t)split * wrows + n0 + quad * 32 + lane] = __uint_as_float(r[0]);
+      else if (n < p.N) atomicAdd(p.dbias + n, __uint_as_float(r[0]));
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int pick_block_c3(int kp) {   // multiple of 16, <= 160 (three accumulators must fit 480 TMEM columns)
+  int best = 16, best_pad = 1 << 30;
+  const int min_tiles = (kp + W3_TAP_COLS - 1) / W3_TAP_COLS;
+  for (int nt = min_tiles; nt <= min_tiles + 3; ++nt) {
+    int bc = ((kp + nt - 1) / nt + 15) / 16 * 16;
+    if (bc > W3_TAP_COLS) continue;
+    if (bc * nt < best_pad) { best_pad = bc * nt; best = bc; }
+  }
+  return best;
+}
+
+// dw[n,c,j] += sum_split ws[split][j][n][c];  dbias[n] += sum_split ws_bias[split][n]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ ws_bias, float* __restrict__ dw,
+                                    float* __restrict__ dbias, int N, int K, int taps, int wrows, int wcols, int nsplit,
+                                    long long sn, long long sk, long long sj) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y, j = blockIdx.z;
+  if (c < K) {
+    float acc = 0.f;
+    for (int s = 0; s < nsplit; ++s) acc += ws[(((size_t)s * taps + j) * wrows + n) * wcols + c];
+    dw[(long long)n * sn + (long long)c * sk + (long long)j * sj] += acc;
+  }
+  if (ws_bias && j == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int s = 0; s < nsplit; ++s) acc += ws_bias[(size_t)s * wrows + n];
+    dbias[n] += acc;
+  }
+}
+
+// workspace plan for the split-K partials; returns bytes needed (0 = use atomics)
+static size_t ws_plan(int nsplit, int taps, int n_tiles, int c_tiles, int block_c, bool bias, size_t* bias_off) {
+  if (nsplit <= 1) return 0;
+  const size_t wrows = (size_t)n_tiles * BLOCK_MN, wcols = (size_t)c_tiles * block_c;
+  size_t bytes = (size_t)nsplit * taps * wrows * wcols * sizeof(float);
+  *bias_off = bytes;
+  if (bias) bytes += (size_t)nsplit * wrows * sizeof(float);
+  return bytes;
 }
 
 int pick_block_c(int kp) {
@@ -202,7 +415,68 @@ bool conv_wgrad_tc_supported(const sd_wgrad_args& a) {
   return true;
 }
 
+static int conv_wgrad3_tc(const sd_wgrad_args& a, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Wg3Params p;
+  memset(&p, 0, sizeof(p));
+  p.dw = a.dw; p.dbias = a.dbias; p.sample_order = a.sample_order; p.group_offsets = a.group_offsets;
+  p.B = a.B; p.T = a.T; p.N = a.N; p.K = a.K; p.dil = a.dil; p.G = a.G;
+  p.gs = a.gs; p.sn = a.sn; p.sk = a.sk; p.sj = a.sj;
+  p.block_c = pick_block_c3(a.Kp);
+  p.c_atoms = (p.block_c + 63) / 64;
+  p.n_tiles = (a.Np + BLOCK_MN - 1) / BLOCK_MN;
+  p.c_tiles = (a.Kp + p.block_c - 1) / p.block_c;
+  const int base_items = p.n_tiles * p.c_tiles * a.G;
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int nsplit = a.G > 1 ? 1 : sms / base_items;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > a.B) nsplit = a.B;
+  p.nsplit = nsplit;
+  p.brows = (BLOCK_T + 2 * a.dil + 7) / 8 * 8;
+  p.batom_bytes = p.brows * 128;
+  p.stage_bytes = 2 * ATOM_BYTES + p.c_atoms * p.batom_bytes;
+  const int smem_bytes = W3_STAGES * p.stage_bytes + ONES_BYTES + 256 + 1024;
+  CUtensorMap tdy, tx;
+  if (make_tmap_3d(&tdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.dout, (uint64_t)a.Np, (uint64_t)a.T, (uint64_t)a.B,
+                   (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, 64, BLOCK_T, 1))
+    return 1;
+  if (make_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, (uint64_t)a.Kp, (uint64_t)a.T, (uint64_t)a.B,
+                   (uint64_t)a.Kp * 2, (uint64_t)a.T * a.Kp * 2, 64, (uint32_t)(BLOCK_T + 2 * a.dil), 1))
+    return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SD_CUDA(cudaFuncSetAttribute(conv_wgrad3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  size_t bias_off = 0;
+  const size_t need = ws_plan(nsplit, 3, p.n_tiles, p.c_tiles, p.block_c, a.dbias != nullptr, &bias_off);
+  const bool use_ws = need > 0 && ws != nullptr && ws_bytes >= need && a.G == 1;
+  p.ws = use_ws ? reinterpret_cast<float*>(ws) : nullptr;
+  p.ws_bias = (use_ws && a.dbias) ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + bias_off) : nullptr;
+  conv_wgrad3_tc_kernel<<<base_items * nsplit, NUM_THREADS, smem_bytes, st>>>(tdy, tx, p);
+  if (check_launch("conv_wgrad3_tc")) return 1;
+  if (use_ws) {
+    wgrad_reduce_kernel<<<dim3(cdiv(a.K, 128), a.N, 3), 128, 0, st>>>(p.ws, p.ws_bias, a.dw, a.dbias, a.N, a.K, 3, p.n_tiles * BLOCK_MN,
+                                                                      p.c_tiles * p.block_c, nsplit, a.sn, a.sk, a.sj);
+    return check_launch("wgrad_reduce");
+  }
+  return 0;
+}
+
 int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
+  void* ws = a.workspace;
+  const size_t ws_bytes = (size_t)a.workspace_bytes;
+  // k=3: shared halo tile for the three taps, as long as the stage ring fits in shared memory
+  if (a.taps == 3) {
+    const int bc = pick_block_c3(a.Kp), atoms = (bc + 63) / 64;
+    const int brows = (BLOCK_T + 2 * a.dil + 7) / 8 * 8;
+    const int smem = W3_STAGES * (2 * ATOM_BYTES + atoms * brows * 128) + ONES_BYTES + 256 + 1024;
+    if (smem <= 227 * 1024 && BLOCK_T + 2 * a.dil <= 256) return conv_wgrad3_tc(a, ws, ws_bytes, st);
+  }
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.dw = a.dw; p.dbias = a.dbias; p.sample_order = a.sample_order; p.group_offsets = a.group_offsets;
@@ -238,8 +512,19 @@ int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
     SD_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  size_t bias_off = 0;
+  const size_t need = ws_plan(nsplit, a.taps, p.n_tiles, p.c_tiles, p.block_c, a.dbias != nullptr, &bias_off);
+  const bool use_ws = need > 0 && ws != nullptr && ws_bytes >= need && a.G == 1;
+  p.ws = use_ws ? reinterpret_cast<float*>(ws) : nullptr;
+  p.ws_bias = (use_ws && a.dbias) ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + bias_off) : nullptr;
   conv_wgrad_tc_kernel<<<base_items * nsplit, NUM_THREADS, smem_bytes, st>>>(tdy, tx, p);
-  return check_launch("conv_wgrad_tc");
+  if (check_launch("conv_wgrad_tc")) return 1;
+  if (use_ws) {
+    wgrad_reduce_kernel<<<dim3(cdiv(a.K, 128), a.N, a.taps), 128, 0, st>>>(p.ws, p.ws_bias, a.dw, a.dbias, a.N, a.K, a.taps,
+                                                                          p.n_tiles * BLOCK_MN, p.c_tiles * p.block_c, nsplit, a.sn, a.sk, a.sj);
+    return check_launch("wgrad_reduce");
+  }
+  return 0;
 }
 
 }  // namespace sd

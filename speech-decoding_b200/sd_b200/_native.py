@@ -28,7 +28,8 @@ class WgradArgs(C.Structure):
                 ("group_offsets", vp),
                 ("B", i32), ("T", i32), ("K", i32), ("Kp", i32), ("N", i32), ("Np", i32),
                 ("taps", i32), ("dil", i32), ("G", i32),
-                ("gs", i64), ("sn", i64), ("sk", i64), ("sj", i64), ("dtype", i32)]
+                ("gs", i64), ("sn", i64), ("sk", i64), ("sj", i64), ("dtype", i32),
+                ("workspace", vp), ("workspace_bytes", i64)]
 
 
 class PackEntry(C.Structure):

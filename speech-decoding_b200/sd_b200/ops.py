@@ -86,15 +86,27 @@ def conv_fwd(inp, w, *, K, N, taps=1, dil=1, bias=None, res=None, widx=None, G=1
     return out
 
 
+_WS = {}
+
+
+def _wgrad_workspace(device):
+    """persistent split-K scratch (64 MB) for the tensor-core wgrad kernels, one per device"""
+    key = (device.type, device.index)
+    if key not in _WS:
+        _WS[key] = torch.empty(16 * 1024 * 1024, dtype=torch.float32, device=device)
+    return _WS[key]
+
+
 def conv_wgrad(dout, inp, dw, *, K, N, taps=1, dil=1, dbias=None, order=None, offsets=None, G=1,
                strides=None):
     B, T, Np = dout.shape
     Kp = inp.shape[2]
     if strides is None:                      # PyTorch Conv1d weight (N, K, taps)
         strides = (N * K * taps, K * taps, taps, 1)
+    ws = _wgrad_workspace(dout.device) if dout.dtype == torch.bfloat16 and G == 1 else None
     a = nat.WgradArgs(_p(dout), _p(inp), _p(dw), _p(dbias), _p(order), _p(offsets),
                       B, T, K, Kp, N, Np, taps, dil, G, strides[0], strides[1], strides[2], strides[3],
-                      code_of(dout))
+                      code_of(dout), _p(ws), ws.numel() * 4 if ws is not None else 0)
     nat.call("sd_conv_wgrad", a, _st())
 
 
