@@ -202,6 +202,10 @@ constexpr int W3_STAGES = 4;
 constexpr int W3_TAP_COLS = 160;
 constexpr int W3_BIAS_COL = 480;
 
+struct WsMaps {
+  CUtensorMap m[2];   // split-K workspace as (wcols, wrows, nsplit*taps) fp32; box (w_h, 32, 1) for the two column halves
+};
+
 struct Wg3Params {
   float* dw;
   float* dbias;
@@ -209,18 +213,18 @@ struct Wg3Params {
   const int* group_offsets;
   int B, T, N, K, dil, G;
   long long gs, sn, sk, sj;
-  int block_c, c_atoms, n_tiles, c_tiles, nsplit, stage_bytes, brows, batom_bytes;
+  int block_c, c_atoms, n_tiles, c_tiles, nsplit, stage_bytes, brows, batom_bytes, ring_bytes;
   float* ws;
   float* ws_bias;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
-                      const Wg3Params p) {
+                      const __grid_constant__ WsMaps wm, const Wg3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t ones_base = smem_base + W3_STAGES * p.stage_bytes;
+  const uint32_t ones_base = smem_base + p.ring_bytes;
   const uint32_t bar_base = ones_base + ONES_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (W3_STAGES + s); };
@@ -252,7 +256,7 @@ conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     fence_barrier_init();
   }
   {
-    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + W3_STAGES * p.stage_bytes);
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_gen + p.ring_bytes);
     for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NUM_THREADS) ones[i] = 0x3F803F80u;
     fence_proxy_async();
   }
@@ -321,23 +325,48 @@ conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     float* dwn = p.dw + (long long)g * p.gs + (long long)n * p.sn;
-    const int wcols = p.c_tiles * p.block_c, wrows = p.n_tiles * BLOCK_MN;
+    const int wrows = p.n_tiles * BLOCK_MN;
+    if (p.ws) {
+      // split-K partial tile -> workspace through shared memory (the stage ring is free now) and one TMA
+      // tensor store per warp and tap: full-line writes instead of 16-byte scattered stores
+      const int seg_cols = (ch1 - ch0) * 16;
+      const uint32_t seg_bytes = (uint32_t)seg_cols * 4;
+      const uint32_t wbase = smem_base + (uint32_t)ew * 2u * 32u * (uint32_t)(W3_TAP_COLS / 2) * 4u;   // two ping-pong tiles per warp
 #pragma unroll 1
-    for (int j = 0; j < 3; ++j) {
-      float* wsn = p.ws ? p.ws + (((size_t)split * 3 + j) * wrows + (n0 + quad * 32 + lane)) * wcols + c0 : nullptr;
-      for (int c = ch0; c < ch1; ++c) {
-        uint32_t r[16];
-        tmem_ld16(taddr + j * W3_TAP_COLS + c * 16, r);
-        tmem_ld_wait();
-        if (wsn) {
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t tile = wbase + (uint32_t)(j & 1) * 32u * (uint32_t)(W3_TAP_COLS / 2) * 4u;
+        if (j == 2) { if (elect_one_sync()) bulk_wait_read1(); __syncwarp(); }
+        for (int c = ch0; c < ch1; ++c) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j * W3_TAP_COLS + c * 16, r);
+          tmem_ld_wait();
+          const uint32_t dst = tile + lane * seg_bytes + (uint32_t)(c - ch0) * 64;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(wsn + c * 16 + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-        } else if (n < p.N) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16 * q), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one_sync()) {
+          if (seg_cols > 0) tma_store_3d(&wm.m[hsel], tile, c0 + ch0 * 16, n0 + quad * 32, split * 3 + j);
+          bulk_commit();
+        }
+      }
+      if (elect_one_sync()) bulk_wait0();
+      __syncwarp();
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        for (int c = ch0; c < ch1; ++c) {
+          uint32_t r[16];
+          tmem_ld16(taddr + j * W3_TAP_COLS + c * 16, r);
+          tmem_ld_wait();
+          if (n < p.N) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int cc = c0 + c * 16 + i;
-            if (cc < p.K) atomicAdd(dwn + (long long)cc * p.sk + (long long)j * p.sj, __uint_as_float(r[i]));
+            for (int i = 0; i < 16; ++i) {
+              const int cc = c0 + c * 16 + i;
+              if (cc < p.K) atomicAdd(dwn + (long long)cc * p.sk + (long long)j * p.sj, __uint_as_float(r[i]));
+            }
           }
         }
       }
@@ -439,7 +468,9 @@ static int conv_wgrad3_tc(const sd_wgrad_args& a, void* ws, size_t ws_bytes, cud
   p.brows = (BLOCK_T + 2 * a.dil + 7) / 8 * 8;
   p.batom_bytes = p.brows * 128;
   p.stage_bytes = 2 * ATOM_BYTES + p.c_atoms * p.batom_bytes;
-  const int smem_bytes = W3_STAGES * p.stage_bytes + ONES_BYTES + 256 + 1024;
+  const int epi_bytes = NUM_EPI_WARPS * 2 * 32 * (W3_TAP_COLS / 2) * 4;     // fp32 staging tiles of the epilogue
+  p.ring_bytes = W3_STAGES * p.stage_bytes > epi_bytes ? W3_STAGES * p.stage_bytes : epi_bytes;
+  const int smem_bytes = p.ring_bytes + ONES_BYTES + 256 + 1024;
   CUtensorMap tdy, tx;
   if (make_tmap_3d(&tdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.dout, (uint64_t)a.Np, (uint64_t)a.T, (uint64_t)a.B,
                    (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, 64, BLOCK_T, 1))
@@ -457,7 +488,20 @@ static int conv_wgrad3_tc(const sd_wgrad_args& a, void* ws, size_t ws_bytes, cud
   const bool use_ws = need > 0 && ws != nullptr && ws_bytes >= need && a.G == 1;
   p.ws = use_ws ? reinterpret_cast<float*>(ws) : nullptr;
   p.ws_bias = (use_ws && a.dbias) ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + bias_off) : nullptr;
-  conv_wgrad3_tc_kernel<<<base_items * nsplit, NUM_THREADS, smem_bytes, st>>>(tdy, tx, p);
+  WsMaps wm;
+  memset(&wm, 0, sizeof(wm));
+  if (use_ws) {
+    const int nch = p.block_c / 16;
+    const int widths[2] = {(nch + 1) / 2 * 16, nch / 2 * 16};
+    const uint64_t wcols = (uint64_t)p.c_tiles * p.block_c, wrows = (uint64_t)p.n_tiles * BLOCK_MN;
+    for (int h = 0; h < 2; ++h) {
+      if (widths[h] == 0) { wm.m[h] = wm.m[0]; continue; }
+      if (make_tmap_3d(&wm.m[h], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.ws, wcols, wrows, (uint64_t)nsplit * 3, wcols * 4, wcols * wrows * 4,
+                       (uint32_t)widths[h], 32, 1, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return 1;
+    }
+  }
+  conv_wgrad3_tc_kernel<<<base_items * nsplit, NUM_THREADS, smem_bytes, st>>>(tdy, tx, wm, p);
   if (check_launch("conv_wgrad3_tc")) return 1;
   if (use_ws) {
     wgrad_reduce_kernel<<<dim3(cdiv(a.K, 128), a.N, 3), 128, 0, st>>>(p.ws, p.ws_bias, a.dw, a.dbias, a.N, a.K, 3, p.n_tiles * BLOCK_MN,
@@ -474,7 +518,9 @@ int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
   if (a.taps == 3) {
     const int bc = pick_block_c3(a.Kp), atoms = (bc + 63) / 64;
     const int brows = (BLOCK_T + 2 * a.dil + 7) / 8 * 8;
-    const int smem = W3_STAGES * (2 * ATOM_BYTES + atoms * brows * 128) + ONES_BYTES + 256 + 1024;
+    int smem = W3_STAGES * (2 * ATOM_BYTES + atoms * brows * 128);
+    if (smem < NUM_EPI_WARPS * 2 * 32 * (W3_TAP_COLS / 2) * 4) smem = NUM_EPI_WARPS * 2 * 32 * (W3_TAP_COLS / 2) * 4;
+    smem += ONES_BYTES + 256 + 1024;
     if (smem <= 227 * 1024 && BLOCK_T + 2 * a.dil <= 256) return conv_wgrad3_tc(a, ws, ws_bytes, st);
   }
   WgParams p;
