@@ -20,6 +20,7 @@
 // synchronisation is a __syncwarp.
 // Persistent grid: one CTA per SM looping over tiles, n-tiles of the same rows adjacent in time so
 // the activation slab is re-read from L2, not HBM.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace sd {
@@ -31,7 +32,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int MAX_BLOCK_N = 256;
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_A_SLOTS = 4, MAX_W_SLOTS = 8;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_EPI_WARPS = 8;
@@ -51,7 +52,7 @@ struct FwdParams {
   int block_n, n_tiles, m_tiles_per_sample, num_tiles, k_blocks;
   int act, out_mode, D2, Op;
   // shared-memory plan (byte offsets from the 1024-aligned base)
-  int stages, stage_bytes, w0cols, off_stg0, off_stg1, off_bias, off_stats, off_bar, cols_alloc;
+  int dbg, sa_slots, sw_slots, a_bytes, w_bytes, a_rows, halo, off_w, w0cols, off_stg0, off_stg1, off_bias, off_stats, off_bar, cols_alloc;
 };
 
 // tensor maps of the epilogue tensors, one per column-half of the tile (the halves may differ in width)
@@ -147,13 +148,16 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
   const uint32_t bar_base = smem_base + p.off_bar;
-  // barrier layout (8 B each): full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], res[8], tmem ptr
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
-  auto res_bar = [&](int w) { return bar_base + 8u * (2 * MAX_STAGES + 4 + w); };
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * MAX_STAGES + 4 + NUM_EPI_WARPS);
+  // barrier layout (8 B each): a_full[4], a_empty[4], w_full[8], w_empty[8], tmem_full[2], tmem_empty[2], res[8], tmem ptr
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (MAX_A_SLOTS + s); };
+  auto wfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_A_SLOTS + s); };
+  auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_A_SLOTS + MAX_W_SLOTS + s); };
+  constexpr int NB = 2 * MAX_A_SLOTS + 2 * MAX_W_SLOTS;
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (NB + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (NB + 2 + a); };
+  auto res_bar = [&](int w) { return bar_base + 8u * (NB + 4 + w); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (NB + 4 + NUM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool glu = p.act == SD_ACT_GLU;
@@ -162,10 +166,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
+    for (int s = 0; s < p.sa_slots; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < p.sw_slots; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), NUM_EPI_WARPS);
@@ -195,13 +197,17 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-  const int k_iters = p.taps * p.k_blocks;
 
+  // Two operand rings.  A ring: one activation tile per k-block, (128 + 2*halo) time rows x 64 channels, loaded
+  // ONCE for all taps (halo = dilation for k=3): tap j is the same tile read from row j*dil on -- SWIZZLE_128B
+  // descriptors take any 128-byte row offset (profiles/r1_probe_umma_desc_row_offset.txt).  W ring: one
+  // BLOCK_N x 64 weight tile per (k-block, tap).  This cuts the L2->SM operand bytes per k-block from
+  // 3*(16+W) KB to (16+4*halo/16)+3*W KB; the kernel is bound by that ingest rate (~62 B/clk/SM measured).
   if (warp == 0) {
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
-    int s = 0;
-    uint32_t ph = 0;
-    const uint32_t stage_tx = A_BYTES + (uint32_t)p.block_n * BLOCK_K * 2;
+    int sa = 0, sw = 0;
+    uint32_t pha = 0, phw = 0;
+    const uint32_t a_tx = (uint32_t)p.a_rows * 128u, w_tx = (uint32_t)p.block_n * BLOCK_K * 2;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
       const int b = m_idx / p.m_tiles_per_sample;
@@ -209,19 +215,24 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int g = p.widx ? __ldg(p.widx + b) : 0;
       const int row0 = glu ? n_idx * half_n : n_idx * p.block_n;
       const int row1 = glu ? p.D2 + n_idx * half_n : row0 + half_n;
-      for (int j = 0; j < p.taps; ++j) {
-        const int shift = (j - (p.taps - 1) / 2) * p.dil;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(aempty_bar(sa), pha ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(afull_bar(sa), a_tx);
+          tma_load_3d(smem_base + sa * p.a_bytes, &tmap_a, afull_bar(sa), kb * BLOCK_K, t0 - p.halo, b);
+        }
+        __syncwarp();
+        if (++sa == p.sa_slots) { sa = 0; pha ^= 1; }
+        for (int j = 0; j < p.taps; ++j) {
+          mbar_wait(wempty_bar(sw), phw ^ 1);
           if (elect_one_sync()) {
-            const uint32_t sa = smem_base + s * p.stage_bytes, sb = sa + A_BYTES;
-            mbar_arrive_expect_tx(full_bar(s), stage_tx);
-            tma_load_3d(sa, &tmap_a, full_bar(s), kb * BLOCK_K, t0 + shift, b);
-            tma_load_3d(sb, &tmap_w, full_bar(s), kb * BLOCK_K, row0, g * p.taps + j);
-            tma_load_3d(sb + half_n * (BLOCK_K * 2), &tmap_w, full_bar(s), kb * BLOCK_K, row1, g * p.taps + j);
+            const uint32_t sb = smem_base + p.off_w + sw * p.w_bytes;
+            mbar_arrive_expect_tx(wfull_bar(sw), w_tx);
+            tma_load_3d(sb, &tmap_w, wfull_bar(sw), kb * BLOCK_K, row0, g * p.taps + j);
+            tma_load_3d(sb + half_n * (BLOCK_K * 2), &tmap_w, wfull_bar(sw), kb * BLOCK_K, row1, g * p.taps + j);
           }
           __syncwarp();
-          if (++s == p.stages) { s = 0; ph ^= 1; }
+          if (++sw == p.sw_slots) { sw = 0; phw ^= 1; }
         }
       }
     }
@@ -229,30 +240,52 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================== MMA issuer (whole warp, one elected lane issues) =====================
     const uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, BLOCK_M, (uint32_t)p.block_n);
     const uint32_t dhi = smem_desc_hi(1024);
-    int s = 0;
-    uint32_t ph = 0;
+    const uint32_t tap_step = (uint32_t)(p.halo * 128) >> 4;   // descriptor units per tap (taps==3: halo == dil)
+    int sa = 0, sw = 0;
+    uint32_t pha = 0, phw = 0;
     int it_tile = 0;
+    long long d_te = 0, d_af = 0, d_wf = 0, d_is = 0, d_t0 = clock64();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
       const int acc = it_tile & 1;
       const uint32_t acc_ph = (it_tile >> 1) & 1;
+      long long q0 = clock64();
       mbar_wait(tempty_bar(acc), acc_ph ^ 1);
       tc_fence_after();
+      d_te += clock64() - q0;
       const uint32_t d_tmem = tmem_base + acc * MAX_BLOCK_N;
-      for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t alo = smem_desc_lo(smem_base + s * p.stage_bytes, 16), blo = alo + (A_BYTES >> 4);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        long long q1 = clock64();
+        mbar_wait(afull_bar(sa), pha);
+        d_af += clock64() - q1;
+        const uint32_t alo = smem_desc_lo(smem_base + sa * p.a_bytes, 16);
+        for (int j = 0; j < p.taps; ++j) {
+          long long q2 = clock64();
+          mbar_wait(wfull_bar(sw), phw);
+          tc_fence_after();
+          long long q3 = clock64();
+          d_wf += q3 - q2;
+          if (elect_one_sync()) {
+            const uint32_t blo = smem_desc_lo(smem_base + p.off_w + sw * p.w_bytes, 16);
+            const uint32_t aj = alo + j * tap_step;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)   // +32 B per 16-element k-step inside the swizzled row
-            umma_f16(d_tmem, desc64(alo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
-          umma_commit(empty_bar(s));
-          if (it == k_iters - 1) umma_commit(tfull_bar(acc));
+            for (int k = 0; k < BLOCK_K / 16; ++k)   // +32 B per 16-element k-step inside the swizzled row
+              umma_f16(d_tmem, desc64(aj + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (kb | j | k) != 0);
+            umma_commit(wempty_bar(sw));
+            if (j == p.taps - 1) {
+              umma_commit(aempty_bar(sa));
+              if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
+            }
+          }
+          __syncwarp();
+          d_is += clock64() - q3;
+          if (++sw == p.sw_slots) { sw = 0; phw ^= 1; }
         }
-        __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+        if (++sa == p.sa_slots) { sa = 0; pha ^= 1; }
       }
     }
+    if (p.dbg >= 2 && lane == 0 && (blockIdx.x % 49) == 0)
+      printf("blk %d mma: tiles %d total %lld | wait tmem-empty %lld a-full %lld w-full %lld | issue %lld (per k-block-tap %.0f)\n", (int)blockIdx.x,
+             it_tile, clock64() - d_t0, d_te, d_af, d_wf, d_is, (double)d_is / (it_tile * p.k_blocks * p.taps));
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;
@@ -281,6 +314,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const CUtensorMap* m_res = &em.res[hsel];
     const CUtensorMap* m_preb = &em.preb[hsel];
     uint32_t res_ph = 0;
+    long long d_ew = 0, d_ework = 0;
 
     int it_tile = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
@@ -309,14 +343,18 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
       }
+      long long e0 = clock64();
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       if (p.res) {
         mbar_wait(res_bar(ew), res_ph);
         res_ph ^= 1;
       }
+      long long e1 = clock64();
+      d_ew += e1 - e0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * MAX_BLOCK_N;
       float sumsq = 0.f;
+      float* nct_row = p.out_nct + (size_t)b * p.N * p.T + (valid ? t : 0);
 
       if (!glu) {
         for (int c = ch0; c < ch1; ++c) {
@@ -339,13 +377,22 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             sts16_bf16(my0 + so, v);
           }
           if (p.out_mode == SD_OUT_NCT_F32 && valid) {
+            float* dst = nct_row + (size_t)nb * p.T;        // Z[b, nb.., t]: lanes = consecutive t => 128-byte stores
+            if (nb + 16 <= p.N) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.N) p.out_nct[((size_t)b * p.N + nb + i) * p.T + t] = v[i];
-            if (p.rownorm2) {
+              for (int i = 0; i < 16; ++i) {
+                *dst = v[i];
+                dst += p.T;
+                sumsq = fmaf(v[i], v[i], sumsq);
+              }
+            } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (nb + i < p.N) sumsq += v[i] * v[i];
+              for (int i = 0; i < 16; ++i) {
+                if (nb + i < p.N) {
+                  dst[(size_t)i * p.T] = v[i];
+                  sumsq = fmaf(v[i], v[i], sumsq);
+                }
+              }
             }
           }
         }
@@ -403,8 +450,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             sts16_bf16(my0 + so, va);
             sts16_bf16(my0b + so, vb);
           }
+          if (cb + 16 <= p.D2) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) va[i] = (cb + i < p.D2) ? va[i] * sigmoid_f(vb[i]) : 0.f;
+            for (int i = 0; i < 16; ++i) va[i] *= sigmoid_fast(vb[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) va[i] = (cb + i < p.D2) ? va[i] * sigmoid_fast(vb[i]) : 0.f;
+          }
           sts16_bf16(my1 + so, va);
         }
         fence_proxy_async();
@@ -427,7 +479,10 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      d_ework += clock64() - e1;
     }
+    if (p.dbg >= 2 && threadIdx.x == 64 && (blockIdx.x % 49) == 0)
+      printf("blk %d epi: tiles %d wait-for-acc %lld work %lld (per tile %.0f)\n", (int)blockIdx.x, it_tile, d_ew, d_ework, (double)d_ework / it_tile);
     if (elect_one_sync()) bulk_wait0();
     __syncwarp();
     if (p.stats) {
@@ -557,7 +612,11 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   p.k_blocks = (a.Kp + BLOCK_K - 1) / BLOCK_K;
 
   // shared-memory plan
-  p.stage_bytes = A_BYTES + p.block_n * BLOCK_K * 2;
+  p.dbg = getenv("SD_DBG") ? atoi(getenv("SD_DBG")) : 0;
+  p.halo = a.taps == 3 ? a.dil : 0;
+  p.a_rows = BLOCK_M + 2 * p.halo;
+  p.a_bytes = (p.a_rows * 128 + 1023) / 1024 * 1024;
+  p.w_bytes = p.block_n * BLOCK_K * 2;
   const int nch = (glu ? p.block_n / 2 : p.block_n) / 16;
   const int w0 = (nch + 1) / 2 * 16, w1 = nch / 2 * 16;          // column widths of the two warp halves
   p.w0cols = w0;
@@ -565,11 +624,18 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   const int stg_bytes = BLOCK_M * p.block_n * 2;
   const int stg1_bytes = need_stg1 ? BLOCK_M * (glu ? p.block_n / 2 : p.block_n) * 2 : 0;
   const int tail = stg_bytes + stg1_bytes + (glu ? 2 : 1) * p.cols_alloc * 4 + 2 * p.cols_alloc * 4 + 512;
-  int stages = (SMEM_LIMIT - 1024 - tail) / p.stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  SD_REQUIRE(stages >= 2, "conv_fwd_tc: not enough shared memory for block_n=%d", p.block_n);
-  p.stages = stages;
-  int off = stages * p.stage_bytes;
+  const int ring = SMEM_LIMIT - 1024 - tail;
+  // taps==3: few activation slots (each feeds 3 weight tiles), the rest of the ring holds weight tiles
+  int sa = a.taps == 3 ? 3 : (ring / (p.a_bytes + p.w_bytes));
+  if (a.taps == 3 && ring - sa * p.a_bytes < 5 * p.w_bytes) sa = 2;
+  if (sa > MAX_A_SLOTS) sa = MAX_A_SLOTS;
+  int sw = (ring - sa * p.a_bytes) / p.w_bytes;
+  if (sw > MAX_W_SLOTS) sw = MAX_W_SLOTS;
+  if (a.taps == 3 && sw > 3 * sa + 3) sw = 3 * sa + 3;
+  SD_REQUIRE(sa >= 1 && sw >= 2 && p.a_rows <= 256, "conv_fwd_tc: operand rings do not fit (block_n=%d dil=%d)", p.block_n, a.dil);
+  p.sa_slots = sa; p.sw_slots = sw;
+  p.off_w = sa * p.a_bytes;
+  int off = p.off_w + sw * p.w_bytes;
   p.off_stg0 = off; off += stg_bytes;
   p.off_stg1 = off; off += stg1_bytes;
   p.off_bias = off; off += (glu ? 2 : 1) * p.cols_alloc * 4;
@@ -616,7 +682,7 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
 
   CUtensorMap ta, tw;
   if (make_tmap_3d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, (uint64_t)a.Kp, (uint64_t)a.T, (uint64_t)a.B,
-                   (uint64_t)a.Kp * 2, (uint64_t)a.T * a.Kp * 2, BLOCK_K, BLOCK_M, 1))
+                   (uint64_t)a.Kp * 2, (uint64_t)a.T * a.Kp * 2, BLOCK_K, (uint32_t)p.a_rows, 1))
     return 1;
   if (make_tmap_3d(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.w, (uint64_t)a.Kp, (uint64_t)a.Np, (uint64_t)a.G * a.taps,
                    (uint64_t)a.Kp * 2, (uint64_t)a.Np * a.Kp * 2, BLOCK_K, (uint32_t)(p.block_n / 2), 1))

@@ -371,7 +371,7 @@ glu_fwd_vec_kernel(const T* __restrict__ y2, T* __restrict__ out, int64_t rows, 
     const int c = (int)(i % nv) * 8;
     F8 a = ld8<T>(y2 + r * 2 * D2 + c), b = ld8<T>(y2 + r * 2 * D2 + D2 + c);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a.v[k] *= sigmoid_f(b.v[k]);
+    for (int k = 0; k < 8; ++k) a.v[k] *= sigmoid_t<T>(b.v[k]);
     st8<T>(out + r * D2 + c, a);
   }
 }
@@ -389,7 +389,7 @@ glu_bwd_vec_kernel(const T* __restrict__ dout, const T* __restrict__ y2, T* __re
     F8 da, db;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float sg = sigmoid_f(b.v[k]);
+      float sg = sigmoid_t<T>(b.v[k]);
       da.v[k] = g.v[k] * sg;
       db.v[k] = g.v[k] * a.v[k] * sg * (1.f - sg);
     }

@@ -464,6 +464,7 @@ static int conv_wgrad3_tc(const sd_wgrad_args& a, void* ws, size_t ws_bytes, cud
   int nsplit = a.G > 1 ? 1 : sms / base_items;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > a.B) nsplit = a.B;
+  if (a.G == 1) nsplit = cdiv(a.B, cdiv(a.B, nsplit));      // drop splits that would get no sample
   p.nsplit = nsplit;
   p.brows = (BLOCK_T + 2 * a.dil + 7) / 8 * 8;
   p.batom_bytes = p.brows * 128;
@@ -542,6 +543,7 @@ int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
   int nsplit = a.G > 1 ? 1 : sms / base_items;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > a.B) nsplit = a.B;
+  if (a.G == 1) nsplit = cdiv(a.B, cdiv(a.B, nsplit));      // drop splits that would get no sample
   p.nsplit = nsplit;
   p.stage_bytes = (2 + p.c_atoms) * ATOM_BYTES;
   const int smem_bytes = STAGES * p.stage_bytes + ONES_BYTES + 256 + 1024;
