@@ -136,10 +136,11 @@ int sd_bn_finalize(const double* stats, int C, int Cp, int64_t n, const float* g
                    float eps, int training, float* ss, void* stream);
 /* u = gelu(y*scale + shift) */
 int sd_bn_gelu_fwd(const void* y, const float* ss, void* u, int64_t rows, int Cp, int dtype, void* stream);
-/* g = du * gelu'(y*scale+shift) written in place over du; red (2,Cp) += sum g, sum g*xhat */
+/* with g = du * gelu'(y*scale+shift) (not stored): red (2,Cp) += sum g, sum g*xhat */
 int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* red, int64_t rows, int Cp,
                           int dtype, void* stream);
-/* dy = scale*(g - sum_g/n - xhat*sum_gx/n) in place over g; also dgamma = sum_gx, dbeta = sum_g (C).
+/* dy = scale*(g - sum_g/n - xhat*sum_gx/n), g recomputed from du and y, written in place over du;
+ * also dgamma = sum_gx, dbeta = sum_g (C).
  * n = n_stat = number of rows the statistics cover (rows * world size under SyncBN).
  * dgamma/dbeta are written as red * dparam_scale (1/world under SyncBN, where red is already the global sum
  * and the parameter gradients are summed across ranks once more afterwards).

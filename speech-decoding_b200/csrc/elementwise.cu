@@ -48,32 +48,6 @@ __global__ void btc_to_nct_kernel(const T* __restrict__ in, float* __restrict__ 
   }
 }
 
-// dZ (B,N,T) fp32 + p (B,T,Np) -> dp (B,T,Np) = dZ^T * gelu'(p)
-template <typename T>
-__global__ void gelu_bwd_nct_kernel(const float* __restrict__ dz, const T* __restrict__ p, T* __restrict__ dp,
-                                    int N, int Tn, int Np) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const float* zb = dz + (size_t)b * N * Tn;
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    int c = c0 + ty + i, t = t0 + tx;
-    tile[ty + i][tx] = (c < N && t < Tn) ? zb[(size_t)c * Tn + t] : 0.f;
-  }
-  __syncthreads();
-  const size_t base = (size_t)b * Tn * Np;
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    int t = t0 + ty + i, c = c0 + tx;
-    if (t < Tn && c < Np) {
-      size_t o = base + (size_t)t * Np + c;
-      float g = (c < N) ? tile[tx][ty + i] * gelu_grad_t<T>(to_f<T>(p[o])) : 0.f;
-      dp[o] = from_f<T>(g);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // weight packing: (N,K,taps) fp32 -> wf (taps,Np,Kp), wd (taps,Kp,Np) taps reversed
 // ---------------------------------------------------------------------------------------------------
@@ -160,7 +134,8 @@ __device__ __forceinline__ F8 ldp8(const float* p) { return ld8<float>(p); }
 constexpr int RED_ROWS = 128;   // rows per block, reduction kernels (fewer blocks => fewer atomics)
 constexpr int EW_ROWS = 64;     // rows per block, pure elementwise channel kernels
 
-// MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce (g written in place over x)
+// MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce over g = du * gelu'(bn(y)) (g is not stored:
+// the apply pass recomputes it, which is cheaper than a 59 MB write + read)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3)
 colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ ss, double* __restrict__ out,
@@ -196,11 +171,9 @@ colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __rest
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float g = v[u].v[i] * gelu_grad_t<T>(fmaf(yy[u].v[i], sc.v[i], sh.v[i]));
-          v[u].v[i] = g;
           a.v[i] += g;
           q.v[i] += g * (yy[u].v[i] - mu.v[i]) * is.v[i];
         }
-        st8<T>(x + rr * Cp + c, v[u]);
       }
     }
   }
@@ -215,6 +188,52 @@ colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __rest
     for (int k = 0; k < R; ++k) { ta += sa[k * Cp + ch]; tq += sq[k * Cp + ch]; }
     atomicAdd(out + ch, (double)ta);
     atomicAdd(out + Cp + ch, (double)tq);
+  }
+}
+
+// dZ (B,N,T) fp32 + p (B,T,Np) -> dp (B,T,Np) = dZ^T * gelu'(p).  64(t) x 64(c) tiles: dZ is read as float4 along
+// t (256 B per 16 lanes), p / dp are accessed as 8-channel vectors (128 B per 8 lanes); Np % 8 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gelu_bwd_nct_kernel(const float* __restrict__ dz, const T* __restrict__ p, T* __restrict__ dp,
+                    int N, int Tn, int Np) {
+  __shared__ float tile[64][65];   // [c][t]
+  const int b = blockIdx.z, t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tid = threadIdx.x;
+  const float* zb = dz + (size_t)b * N * Tn;
+  const bool vec_t = (Tn & 3) == 0;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * 256;           // 64 rows(c) x 16 float4(t)
+    const int cl = idx >> 4, tq = (idx & 15) * 4;
+    const int c = c0 + cl, t = t0 + tq;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < N) {
+      const float* src = zb + (size_t)c * Tn + t;
+      if (vec_t && t + 3 < Tn) v = *reinterpret_cast<const float4*>(src);
+      else {
+        if (t < Tn) v.x = src[0];
+        if (t + 1 < Tn) v.y = src[1];
+        if (t + 2 < Tn) v.z = src[2];
+        if (t + 3 < Tn) v.w = src[3];
+      }
+    }
+    tile[cl][tq] = v.x; tile[cl][tq + 1] = v.y; tile[cl][tq + 2] = v.z; tile[cl][tq + 3] = v.w;
+  }
+  __syncthreads();
+  const size_t base = (size_t)b * Tn * Np;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = tid + it * 256;           // 64 rows(t) x 8 channel-vectors
+    const int tl = idx >> 3, cv = (idx & 7) * 8;
+    const int t = t0 + tl, c = c0 + cv;
+    if (t < Tn && c < Np) {
+      const size_t o = base + (size_t)t * Np + c;
+      F8 pv = ld8<T>(p + o), g;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g.v[i] = (c + i < N) ? tile[cv + i][tl] * gelu_grad_t<T>(pv.v[i]) : 0.f;
+      st8<T>(dp + o, g);
+    }
   }
 }
 
@@ -292,9 +311,9 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
       if (dgamma) dgamma[ch] = (float)red[Cp + ch] * dscale;
     }
   }
-  const F8 sc = ldp8(ss + c), mu = ldp8(ss + 2 * Cp + c), is = ldp8(ss + 3 * Cp + c);
+  const F8 sc = ldp8(ss + c), sh = ldp8(ss + Cp + c), mu = ldp8(ss + 2 * Cp + c), is = ldp8(ss + 3 * Cp + c);
   const float invn = 1.0f / (float)n_stat;
-  // dy = k1*g + k2*y + k3 with per-channel constants
+  // g = du * gelu'(sc*y + sh);  dy = sc*g + k2*y + k3 with per-channel constants
   F8 k2, k3;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -309,7 +328,7 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
       const int64_t rr = r + (int64_t)u * R;
       if (rr < r1) {
         v[u] = ld8<T>(g + rr * Cp + c);
-        if (training) yy[u] = ld8<T>(y + rr * Cp + c);
+        yy[u] = ld8<T>(y + rr * Cp + c);
       }
     }
 #pragma unroll
@@ -317,8 +336,10 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
       const int64_t rr = r + (int64_t)u * R;
       if (rr >= r1) break;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        v[u].v[i] = training ? fmaf(sc.v[i], v[u].v[i], fmaf(k2.v[i], yy[u].v[i], k3.v[i])) : sc.v[i] * v[u].v[i];
+      for (int i = 0; i < 8; ++i) {
+        const float gg = v[u].v[i] * gelu_grad_t<T>(fmaf(yy[u].v[i], sc.v[i], sh.v[i]));
+        v[u].v[i] = training ? fmaf(sc.v[i], gg, fmaf(k2.v[i], yy[u].v[i], k3.v[i])) : sc.v[i] * gg;
+      }
       st8<T>(g + rr * Cp + c, v[u]);
     }
   }
@@ -446,8 +467,9 @@ int sd_btc_to_nct(const void* in, float* out, int B, int C, int T_, int Cp, int 
 }
 
 int sd_gelu_bwd_nct(const float* dz, const void* p, void* dp, int B, int N, int T_, int Np, int dtype, void* stream) {
-  dim3 grid(cdiv(T_, 32), cdiv(Np, 32), B), block(32, 8);
-  DISPATCH_DTYPE(dtype, gelu_bwd_nct_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(dz, (const T*)p, (T*)dp, N, T_, Np));
+  SD_REQUIRE(Np % 8 == 0, "sd_gelu_bwd_nct: Np %% 8 != 0");
+  dim3 grid(cdiv(T_, 64), cdiv(Np, 64), B);
+  DISPATCH_DTYPE(dtype, gelu_bwd_nct_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(dz, (const T*)p, (T*)dp, N, T_, Np));
   return check_launch("gelu_bwd_nct");
 }
 

@@ -27,17 +27,28 @@ sa_weights_fwd_kernel(const float* __restrict__ z_ri, const float* __restrict__ 
   }
   for (int i = tid; i < 2 * K2; i += blockDim.x) zs[i] = z_ri[(size_t)d * 2 * K2 + i];
   __syncthreads();
-  // logits: the K^2-long contraction is split over the 8 warps (fp64 partial sums, combined in smem);
-  // lanes run over sensors so the cos/sin reads are coalesced.
+  // logits: the K^2-long contraction is split over the 8 warps; each lane keeps 4 independent fp32 partial
+  // sums (<= K^2/32 terms each) and the 32 partials per logit are combined in fp64 -- B200's fp64 FMA rate is
+  // ~1/64 of fp32, so the bulk of the sum must not be fp64; the fp32 partials carry ~1e-6 absolute error on
+  // logits of magnitude <= 40, far inside the 1e-4 budget.  Lanes run over sensors: coalesced table reads.
   double* part = reinterpret_cast<double*>(smem + 2 * K2 + ((C + 1) & ~1));   // [8][C]
   {
     const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
     const int m0 = (int)((long long)K2 * warp / nw), m1 = (int)((long long)K2 * (warp + 1) / nw);
     for (int c = lane; c < C; c += 32) {
-      double acc = 0.0;
-      for (int m = m0; m < m1; ++m)
-        acc += (double)zs[2 * m] * (double)cos_t[(size_t)m * C + c] + (double)zs[2 * m + 1] * (double)sin_t[(size_t)m * C + c];
-      part[warp * C + c] = acc;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int m = m0;
+      for (; m + 1 < m1; m += 2) {
+        a0 = fmaf(zs[2 * m], cos_t[(size_t)m * C + c], a0);
+        a1 = fmaf(zs[2 * m + 1], sin_t[(size_t)m * C + c], a1);
+        a2 = fmaf(zs[2 * m + 2], cos_t[(size_t)(m + 1) * C + c], a2);
+        a3 = fmaf(zs[2 * m + 3], sin_t[(size_t)(m + 1) * C + c], a3);
+      }
+      if (m < m1) {
+        a0 = fmaf(zs[2 * m], cos_t[(size_t)m * C + c], a0);
+        a1 = fmaf(zs[2 * m + 1], sin_t[(size_t)m * C + c], a1);
+      }
+      part[warp * C + c] = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
     }
   }
   __syncthreads();
@@ -99,19 +110,21 @@ sa_weights_bwd_kernel(const float* __restrict__ dwm, const float* __restrict__ w
   for (int i = 0; i < nw; ++i) dot += red[i];
   for (int c = tid; c < C; c += blockDim.x) da[c] = w_soft[(size_t)d * C + c] * (da[c] - dot);
   __syncthreads();
-  for (int m = warp; m < K2; m += nw) {
-    float re = 0.f, im = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      float a = da[c];
-      re += a * cos_t[(size_t)m * C + c];
-      im += a * sin_t[(size_t)m * C + c];
+  // z.grad[d,m] = sum_c da[d,c] * (cos[m,c] + i sin[m,c]): one thread per frequency m walks its table rows
+  // (L1/L2-resident: 2 x K^2 x C floats), da[c] is a shared-memory broadcast; no cross-lane reductions.
+  for (int m = blockIdx.y * blockDim.x + tid; m < K2; m += gridDim.y * blockDim.x) {
+    const float* cr = cos_t + (size_t)m * C;
+    const float* sr = sin_t + (size_t)m * C;
+    float re0 = 0.f, re1 = 0.f, im0 = 0.f, im1 = 0.f;
+    int c = 0;
+    for (; c + 1 < C; c += 2) {
+      re0 = fmaf(da[c], cr[c], re0);
+      im0 = fmaf(da[c], sr[c], im0);
+      re1 = fmaf(da[c + 1], cr[c + 1], re1);
+      im1 = fmaf(da[c + 1], sr[c + 1], im1);
     }
-    re = warp_sum(re);
-    im = warp_sum(im);
-    if (lane == 0) {
-      dz_ri[((size_t)d * K2 + m) * 2 + 0] = re;
-      dz_ri[((size_t)d * K2 + m) * 2 + 1] = im;
-    }
+    if (c < C) { re0 = fmaf(da[c], cr[c], re0); im0 = fmaf(da[c], sr[c], im0); }
+    *reinterpret_cast<float2*>(dz_ri + ((size_t)d * K2 + m) * 2) = make_float2(re0 + re1, im0 + im1);
   }
 }
 
@@ -140,7 +153,7 @@ int sd_sa_weights_fwd(const float* z_ri, const float* cos_t, const float* sin_t,
 
 int sd_sa_weights_bwd(const float* dwm, const float* w_soft, const float* mask, const float* cos_t,
                       const float* sin_t, float* dz_ri, int D1, int K2, int C, void* stream) {
-  sa_weights_bwd_kernel<<<D1, 256, C * sizeof(float), (cudaStream_t)stream>>>(dwm, w_soft, mask, cos_t, sin_t, dz_ri, K2, C);
+  sa_weights_bwd_kernel<<<dim3(D1, (K2 + 255) / 256 < 4 ? (K2 + 255) / 256 : 4), 256, C * sizeof(float), (cudaStream_t)stream>>>(dwm, w_soft, mask, cos_t, sin_t, dz_ri, K2, C);
   return check_launch("sa_weights_bwd");
 }
 

@@ -363,8 +363,10 @@ class FinalStage(Stage):
         keep = sv is not None
         p2 = torch.empty((B, T, rup8(Fo)), dtype=dt, device=dev) if keep else None
         Z = torch.empty((B, Fo, T), dtype=torch.float32, device=dev)
+        zn2 = torch.zeros((B,), dtype=torch.float32, device=dev)     # sum of Z^2 per sample, fused into the epilogue
         ops.conv_fwd(u, run.pack.wf(self.key + ".f2"), K=N1, N=Fo, bias=m.conv_final2.bias, out=Z, preact=p2,
-                     act=nat.ACT_GELU, out_mode=nat.OUT_NCT_F32)
+                     rownorm2=zn2, act=nat.ACT_GELU, out_mode=nat.OUT_NCT_F32)
+        run.out_norm2 = zn2
         if keep:
             sv.update(x=x, p1=p1, u=u, p2=p2)
         return Z
@@ -429,6 +431,7 @@ class Pipeline:
         self.dtype = None
         self.gpool = None
         self.scratch = None
+        self.out_norm2 = None       # squared row norms of the pipeline output when the last stage produced them
         self._scratch_n = sum(st.scratch for st in stages)
         self.reducer = None         # dist.GradReducer: per-stage gradient all-reduce (data parallel)
         self.bn_group = None        # process group for SyncBN statistics, or None
@@ -490,7 +493,8 @@ class _PipelineFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pipe, X, *params):
         keep = pipe._keep
-        with torch.cuda.device(X.device):
+        with torch.cuda.device(X.device), ops.stream_scope():
+            pipe.out_norm2 = None
             out, saved = pipe._forward(X, keep)
         ctx.pipe, ctx.saved, ctx.params = pipe, saved, params
         ctx.precision = ops.get_precision()
@@ -504,7 +508,7 @@ class _PipelineFn(torch.autograd.Function):
         prev = ops.get_precision()
         ops.set_precision(ctx.precision)
         try:
-            with torch.cuda.device(dout.device):
+            with torch.cuda.device(dout.device), ops.stream_scope():
                 pipe.dtype = ops.dtypes()[0]
                 dx, grads = pipe._backward(ctx.saved, dout, ctx.needs_input_grad[1])
         finally:

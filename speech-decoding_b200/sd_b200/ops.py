@@ -41,8 +41,25 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+_stream_cache = [None]
+
+
 def _st():
-    return torch.cuda.current_stream().cuda_stream
+    """raw cudaStream_t of torch's current stream.  torch.cuda.current_stream() costs ~15 us per call, so the
+    executor pins the handle for the duration of one forward / backward (see stream_scope)."""
+    s = _stream_cache[0]
+    return s if s is not None else torch.cuda.current_stream().cuda_stream
+
+
+class stream_scope:
+    def __enter__(self):
+        self.prev = _stream_cache[0]
+        _stream_cache[0] = torch.cuda.current_stream().cuda_stream
+        return self
+
+    def __exit__(self, *a):
+        _stream_cache[0] = self.prev
+        return False
 
 
 def require_cuda(t, name):

@@ -187,7 +187,12 @@ class BrainEncoder(nn.Module):
 
     def forward(self, X, subject_idxs):
         ids = engine.normalize_subject_ids(subject_idxs, self.num_subjects)
-        return self.pipeline().run(X, ids)
+        pipe = self.pipeline()
+        Z = pipe.run(X, ids)
+        if pipe.out_norm2 is not None:
+            # |Z_b|^2 came for free from the last conv's epilogue; CLIPLoss picks it up (one pass over Z saved)
+            Z._sd_norm2 = pipe.out_norm2
+        return Z
 
 
 class Classifier(nn.Module):

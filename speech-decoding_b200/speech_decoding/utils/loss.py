@@ -39,13 +39,13 @@ class _ClipFn(torch.autograd.Function):
     data-parallel), z = local brain rows."""
 
     @staticmethod
-    def forward(ctx, x, z, temp, reduction, use_temp, group):
+    def forward(ctx, x, z, temp, reduction, use_temp, group, zn2_hint):
         M, Nn = x.shape[0], z.shape[0]
         world, rank = sd_dist.world_rank(group)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), ops.stream_scope():
             tc = ops.clip_tc_ok(x, z)          # bf16 mode: TF32 tensor-core GEMMs; fp32 mode: exact fp32
             xn2 = ops.rownorm2(x)
-            zn2 = ops.rownorm2(z)
+            zn2 = zn2_hint if zn2_hint is not None else ops.rownorm2(z)
             dots = ops.clip_dots(x, z, tc=tc)
             t = temp.detach() if use_temp else torch.zeros_like(temp)
             logits, row_stat, col_lse = ops.clip_phase1(dots, xn2, zn2, t)
@@ -67,7 +67,7 @@ class _ClipFn(torch.autograd.Function):
     def backward(ctx, gloss, _glogits):
         x, z, coef, cz, partial, logits, xn2, zn2, t, coef_t = ctx.saved_tensors
         dx = dz = dtemp = None
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), ops.stream_scope():
             if ctx.needs_input_grad[1]:
                 gs = gloss.detach().float().reshape(1).contiguous()
                 dz = ops.clip_dz_tc(coef_t, cz, x, z, gs) if ctx.tc else ops.clip_dz(coef, cz, x, z, gs)
@@ -78,7 +78,7 @@ class _ClipFn(torch.autograd.Function):
                 dx = ops.clip_dz(coef.t().contiguous(), cx.contiguous(), z, x, gloss.detach().float().reshape(1).contiguous())
             if ctx.needs_input_grad[2] and ctx.use_temp:
                 dtemp = (partial[1] * gloss).reshape(1)
-        return dx, dz, dtemp, None, None, None
+        return dx, dz, dtemp, None, None, None, None
 
 
 class CLIPLoss(nn.Module):
@@ -112,7 +112,10 @@ class CLIPLoss(nn.Module):
         group = self.process_group
         if group is not None:
             xf = sd_dist.all_gather_rows(xf, group)
-        loss, logits = _ClipFn.apply(xf, yf, self.temp, self.reduction, bool(fast), group)
+        zn2 = getattr(y, "_sd_norm2", None)      # set by BrainEncoder.forward (fused into its last epilogue)
+        if zn2 is not None and (zn2.shape[0] != batch_size or y.dtype != torch.float32):
+            zn2 = None
+        loss, logits = _ClipFn.apply(xf, yf, self.temp, self.reduction, bool(fast), group, zn2)
         if return_logits:
             return (logits if fast else logits.t()), loss
         return loss
