@@ -64,27 +64,30 @@ int sd_btc_to_nct(const void* in, float* out, int B, int C, int T, int Cp, int d
  * Either destination may be NULL. */
 int sd_pack_weight(const float* w, void* wf, void* wd, int N, int K, int taps, int Np, int Kp, int dtype,
                    void* stream);
-/* batched form: `table` is a device array of n entries of sd_pack_entry */
+/* batched form: `table` is a device array of n entries of sd_pack_entry;
+ * max_tiles = max over entries of ceil(Np/32)*ceil(Kp/32) (grid extent; smaller entries exit early) */
 typedef struct {
   const float* w;
   void* wf;
   void* wd;
   int N, K, taps, Np, Kp, dtype;
 } sd_pack_entry;
-int sd_pack_weights(const sd_pack_entry* table, int n, void* stream);
+int sd_pack_weights(const sd_pack_entry* table, int n, int max_tiles, void* stream);
 
 /* ---- SpatialAttention (models.py:45-65) + SpatialDropout (models.py:77-86) -------------------- */
 /* a = Re(z)·cos + Im(z)·sin (models.py:49-53); w = softmax(a, -1) (:58); masked w·mask is what the
  * channel mix uses (dropping input channels == zeroing weight columns).
  *   z_ri (D1,K2,2) interleaved re/im; cos,sin (K2,C); mask (C) or NULL (eval)
  *   w_soft (D1,C) fp32 saved for backward; w_packed (1,D1p,Cp) `dtype` for sd_conv_fwd. */
+#define SD_SA_MPARTS 8 /* frequency partitions of the logits kernel; scratch = SD_SA_MPARTS*D1*C floats */
 int sd_sa_weights_fwd(const float* z_ri, const float* cos_t, const float* sin_t, const float* mask,
-                      float* w_soft, void* w_packed, int D1, int K2, int C, int D1p, int Cp, int dtype,
-                      void* stream);
+                      float* w_soft, void* w_packed, float* scratch, int D1, int K2, int C, int D1p, int Cp,
+                      int dtype, void* stream);
 /* dwm (D1,C) fp32 = gradient w.r.t. the masked mixing weights; dz_ri (D1,K2,2) = z.grad
- * (autograd convention dL/dRe + i dL/dIm). */
-int sd_sa_weights_bwd(const float* dwm, const float* w_soft, const float* mask, const float* cos_t,
-                      const float* sin_t, float* dz_ri, int D1, int K2, int C, void* stream);
+ * (autograd convention dL/dRe + i dL/dIm).  cos_T / sin_T are the TRANSPOSED
+ * tables (C,K2) (the buffers of models.py:39-40 transposed once by the caller) for coalesced access. */
+int sd_sa_weights_bwd(const float* dwm, const float* w_soft, const float* mask, const float* cos_T,
+                      const float* sin_T, float* dz_ri, int D1, int K2, int C, void* stream);
 
 /* ---- implicit-GEMM Conv1d: forward and data-gradient ------------------------------------------ */
 /* out[b,t,n] = act( bias[n] + res[b,t,n] + sum_j sum_k in[b, t+(j-(taps-1)/2)*dil, k] * w[g(b),j,n,k] )

@@ -51,42 +51,53 @@ __global__ void btc_to_nct_kernel(const T* __restrict__ in, float* __restrict__ 
 // ---------------------------------------------------------------------------------------------------
 // weight packing: (N,K,taps) fp32 -> wf (taps,Np,Kp), wd (taps,Kp,Np) taps reversed
 // ---------------------------------------------------------------------------------------------------
+// One 32(n) x 32(k) tile of one weight, all taps: the source rows w[n, k0:k0+32, :] are contiguous (32*taps
+// floats), both destinations are written along their contiguous dimension through a shared-memory tile.
 template <typename T>
-__device__ __forceinline__ void pack_one(const sd_pack_entry& e, int64_t start, int64_t step) {
-  const int64_t total = (int64_t)e.taps * e.Np * e.Kp;
+__device__ __forceinline__ void pack_tile(const sd_pack_entry& e, int tile, float (*t)[32][33]) {
+  const int tiles_k = (e.Kp + 31) / 32, tiles_n = (e.Np + 31) / 32;
+  if (tile >= tiles_k * tiles_n) return;
+  const int n0 = (tile / tiles_k) * 32, k0 = (tile % tiles_k) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int nn = ty; nn < 32; nn += 8) {
+    const int n = n0 + nn;
+    for (int idx = tx; idx < 32 * e.taps; idx += 32) {
+      const int kk = idx / e.taps, j = idx - kk * e.taps;
+      float v = 0.f;
+      if (n < e.N && k0 + kk < e.K) v = e.w[((int64_t)n * e.K + k0) * e.taps + idx];
+      t[j][nn][kk] = v;
+    }
+  }
+  __syncthreads();
   T* wf = reinterpret_cast<T*>(e.wf);
   T* wd = reinterpret_cast<T*>(e.wd);
-  for (int64_t i = start; i < total; i += step) {
+  for (int j = 0; j < e.taps; ++j) {
     if (wf) {
-      int k = (int)(i % e.Kp);
-      int n = (int)((i / e.Kp) % e.Np);
-      int j = (int)(i / ((int64_t)e.Kp * e.Np));
-      float v = (n < e.N && k < e.K) ? e.w[((int64_t)n * e.K + k) * e.taps + j] : 0.f;
-      wf[i] = from_f<T>(v);
+      for (int nn = ty; nn < 32; nn += 8) {
+        const int n = n0 + nn, k = k0 + tx;
+        if (n < e.Np && k < e.Kp) wf[((int64_t)j * e.Np + n) * e.Kp + k] = from_f<T>(t[j][nn][tx]);
+      }
     }
     if (wd) {
-      int n = (int)(i % e.Np);
-      int k = (int)((i / e.Np) % e.Kp);
-      int j = (int)(i / ((int64_t)e.Kp * e.Np));
-      float v = (n < e.N && k < e.K) ? e.w[((int64_t)n * e.K + k) * e.taps + (e.taps - 1 - j)] : 0.f;
-      wd[i] = from_f<T>(v);
+      for (int kk = ty; kk < 32; kk += 8) {
+        const int k = k0 + kk, n = n0 + tx;
+        if (n < e.Np && k < e.Kp) wd[((int64_t)(e.taps - 1 - j) * e.Kp + k) * e.Np + n] = from_f<T>(t[j][tx][kk]);
+      }
     }
   }
 }
 
-__global__ void pack_weights_kernel(const sd_pack_entry* __restrict__ table) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(const sd_pack_entry* __restrict__ table) {
+  __shared__ float t[3][32][33];
   const sd_pack_entry e = table[blockIdx.y];
-  int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t step = (int64_t)gridDim.x * blockDim.x;
-  if (e.dtype == SD_BF16) pack_one<__nv_bfloat16>(e, start, step);
-  else pack_one<float>(e, start, step);
+  if (e.dtype == SD_BF16) pack_tile<__nv_bfloat16>(e, blockIdx.x, t);
+  else pack_tile<float>(e, blockIdx.x, t);
 }
 
-__global__ void pack_weight_single_kernel(sd_pack_entry e) {
-  int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t step = (int64_t)gridDim.x * blockDim.x;
-  if (e.dtype == SD_BF16) pack_one<__nv_bfloat16>(e, start, step);
-  else pack_one<float>(e, start, step);
+__global__ void __launch_bounds__(256) pack_weight_single_kernel(sd_pack_entry e) {
+  __shared__ float t[3][32][33];
+  if (e.dtype == SD_BF16) pack_tile<__nv_bfloat16>(e, blockIdx.x, t);
+  else pack_tile<float>(e, blockIdx.x, t);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -475,15 +486,16 @@ int sd_gelu_bwd_nct(const float* dz, const void* p, void* dp, int B, int N, int 
 
 int sd_pack_weight(const float* w, void* wf, void* wd, int N, int K, int taps, int Np, int Kp, int dtype,
                    void* stream) {
+  SD_REQUIRE(taps >= 1 && taps <= 3, "sd_pack_weight: taps must be 1..3");
   sd_pack_entry e{w, wf, wd, N, K, taps, Np, Kp, dtype};
-  int64_t total = (int64_t)taps * Np * Kp;
-  pack_weight_single_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(e);
+  pack_weight_single_kernel<<<cdiv(Np, 32) * cdiv(Kp, 32), 256, 0, (cudaStream_t)stream>>>(e);
   return check_launch("pack_weight");
 }
 
-int sd_pack_weights(const sd_pack_entry* table, int n, void* stream) {
+int sd_pack_weights(const sd_pack_entry* table, int n, int max_tiles, void* stream) {
   if (n <= 0) return 0;
-  pack_weights_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(table);
+  SD_REQUIRE(max_tiles > 0, "sd_pack_weights: max_tiles = max over entries of ceil(Np/32)*ceil(Kp/32)");
+  pack_weights_kernel<<<dim3(max_tiles, n), 256, 0, (cudaStream_t)stream>>>(table);
   return check_launch("pack_weights");
 }
 

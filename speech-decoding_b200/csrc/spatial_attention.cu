@@ -11,51 +11,64 @@
 
 namespace sd {
 
+constexpr int SA_DT = 16;     // rows of z (output channels d) per block
+constexpr int SA_MC = 128;    // frequencies per shared-memory chunk
+
+// Partial logits: part[mp][d][c] = sum_{m in partition mp} Re z[d,m] cos[m,c] + Im z[d,m] sin[m,c].
+// A block owns SA_DT rows of z and one partition of the K^2 frequencies: every table element it reads
+// (coalesced over sensors c) feeds SA_DT FMAs, so the tables are read ceil(D1/16) times in total instead
+// of D1 times.  fp32 accumulation over <= K^2/parts terms; the partitions are combined in fp64 by the
+// softmax kernel (B200's fp64 FMA rate is ~1/64 of fp32, so fp64 is kept out of the inner loop).
+__global__ void __launch_bounds__(256)
+sa_logits_kernel(const float* __restrict__ z_ri, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                 float* __restrict__ part, int D1, int K2, int C, int mparts) {
+  __shared__ float zs[SA_DT][2 * SA_MC];
+  const int d0 = blockIdx.x * SA_DT, mp = blockIdx.y, tid = threadIdx.x;
+  const int m_lo = (int)((long long)K2 * mp / mparts), m_hi = (int)((long long)K2 * (mp + 1) / mparts);
+  for (int c0 = 0; c0 < C; c0 += 256) {
+    const int c = c0 + tid;
+    float acc[SA_DT];
+#pragma unroll
+    for (int i = 0; i < SA_DT; ++i) acc[i] = 0.f;
+    for (int mc = m_lo; mc < m_hi; mc += SA_MC) {
+      const int mn = min(SA_MC, m_hi - mc);
+      __syncthreads();
+      for (int i = tid; i < SA_DT * 2 * mn; i += 256) {
+        const int dd = i / (2 * mn), r = i % (2 * mn);
+        zs[dd][r] = (d0 + dd < D1) ? z_ri[((size_t)(d0 + dd) * K2 + mc) * 2 + r] : 0.f;
+      }
+      __syncthreads();
+      if (c < C) {
+        for (int m = 0; m < mn; ++m) {
+          const float cv = cos_t[(size_t)(mc + m) * C + c], sv = sin_t[(size_t)(mc + m) * C + c];
+#pragma unroll
+          for (int i = 0; i < SA_DT; ++i) acc[i] = fmaf(zs[i][2 * m], cv, fmaf(zs[i][2 * m + 1], sv, acc[i]));
+        }
+      }
+    }
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < SA_DT; ++i)
+        if (d0 + i < D1) part[((size_t)mp * D1 + d0 + i) * C + c] = acc[i];
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-sa_weights_fwd_kernel(const float* __restrict__ z_ri, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
-                      const float* __restrict__ mask, float* __restrict__ w_soft, T* __restrict__ w_packed, int D1,
-                      int K2, int C, int Cp) {
-  extern __shared__ float smem[];
-  float* zs = smem;               // 2*K2 interleaved re/im
-  float* logit = smem + 2 * K2;   // C
+sa_softmax_kernel(const float* __restrict__ part, const float* __restrict__ mask, float* __restrict__ w_soft,
+                  T* __restrict__ w_packed, int D1, int C, int Cp, int mparts) {
+  extern __shared__ float logit[];   // C
   __shared__ float red[32];
   const int d = blockIdx.x, tid = threadIdx.x;
   if (d >= D1) {  // zero rows of the padded weight matrix
     for (int c = tid; c < Cp; c += blockDim.x) w_packed[(size_t)d * Cp + c] = from_f<T>(0.f);
     return;
   }
-  for (int i = tid; i < 2 * K2; i += blockDim.x) zs[i] = z_ri[(size_t)d * 2 * K2 + i];
-  __syncthreads();
-  // logits: the K^2-long contraction is split over the 8 warps; each lane keeps 4 independent fp32 partial
-  // sums (<= K^2/32 terms each) and the 32 partials per logit are combined in fp64 -- B200's fp64 FMA rate is
-  // ~1/64 of fp32, so the bulk of the sum must not be fp64; the fp32 partials carry ~1e-6 absolute error on
-  // logits of magnitude <= 40, far inside the 1e-4 budget.  Lanes run over sensors: coalesced table reads.
-  double* part = reinterpret_cast<double*>(smem + 2 * K2 + ((C + 1) & ~1));   // [8][C]
-  {
-    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-    const int m0 = (int)((long long)K2 * warp / nw), m1 = (int)((long long)K2 * (warp + 1) / nw);
-    for (int c = lane; c < C; c += 32) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int m = m0;
-      for (; m + 1 < m1; m += 2) {
-        a0 = fmaf(zs[2 * m], cos_t[(size_t)m * C + c], a0);
-        a1 = fmaf(zs[2 * m + 1], sin_t[(size_t)m * C + c], a1);
-        a2 = fmaf(zs[2 * m + 2], cos_t[(size_t)(m + 1) * C + c], a2);
-        a3 = fmaf(zs[2 * m + 3], sin_t[(size_t)(m + 1) * C + c], a3);
-      }
-      if (m < m1) {
-        a0 = fmaf(zs[2 * m], cos_t[(size_t)m * C + c], a0);
-        a1 = fmaf(zs[2 * m + 1], sin_t[(size_t)m * C + c], a1);
-      }
-      part[warp * C + c] = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
-    }
-  }
-  __syncthreads();
   float lmax = -INFINITY;
   for (int c = tid; c < C; c += blockDim.x) {
     double acc = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += part[w * C + c];
+    for (int mp = 0; mp < mparts; ++mp) acc += (double)part[((size_t)mp * D1 + d) * C + c];
     logit[c] = (float)acc;
     lmax = fmaxf(lmax, (float)acc);
   }
@@ -89,43 +102,45 @@ sa_weights_fwd_kernel(const float* __restrict__ z_ri, const float* __restrict__ 
 }
 
 // dw~ -> da (softmax backward through the mask) -> z.grad = da·cos^T + i da·sin^T   (appendix A.1)
+// Block = SA_DT rows d x 256 frequencies m; thread = frequency m with 2*SA_DT accumulators; the tables are
+// read through their TRANSPOSES (C, K^2) so that lanes (consecutive m) are coalesced; da is a smem broadcast.
 __global__ void __launch_bounds__(256)
 sa_weights_bwd_kernel(const float* __restrict__ dwm, const float* __restrict__ w_soft, const float* __restrict__ mask,
-                      const float* __restrict__ cos_t, const float* __restrict__ sin_t, float* __restrict__ dz_ri,
-                      int K2, int C) {
-  extern __shared__ float da[];  // C
-  __shared__ float red[32];
-  const int d = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  float dot = 0.f;
-  for (int c = tid; c < C; c += blockDim.x) {
-    float g = dwm[(size_t)d * C + c] * (mask ? mask[c] : 1.f);
-    float w = w_soft[(size_t)d * C + c];
-    da[c] = g;
-    dot += g * w;
-  }
-  dot = warp_sum(dot);
-  if (lane == 0) red[warp] = dot;
-  __syncthreads();
-  dot = 0.f;
-  for (int i = 0; i < nw; ++i) dot += red[i];
-  for (int c = tid; c < C; c += blockDim.x) da[c] = w_soft[(size_t)d * C + c] * (da[c] - dot);
-  __syncthreads();
-  // z.grad[d,m] = sum_c da[d,c] * (cos[m,c] + i sin[m,c]): one thread per frequency m walks its table rows
-  // (L1/L2-resident: 2 x K^2 x C floats), da[c] is a shared-memory broadcast; no cross-lane reductions.
-  for (int m = blockIdx.y * blockDim.x + tid; m < K2; m += gridDim.y * blockDim.x) {
-    const float* cr = cos_t + (size_t)m * C;
-    const float* sr = sin_t + (size_t)m * C;
-    float re0 = 0.f, re1 = 0.f, im0 = 0.f, im1 = 0.f;
-    int c = 0;
-    for (; c + 1 < C; c += 2) {
-      re0 = fmaf(da[c], cr[c], re0);
-      im0 = fmaf(da[c], sr[c], im0);
-      re1 = fmaf(da[c + 1], cr[c + 1], re1);
-      im1 = fmaf(da[c + 1], sr[c + 1], im1);
+                      const float* __restrict__ cosT, const float* __restrict__ sinT, float* __restrict__ dz_ri,
+                      int D1, int K2, int C) {
+  extern __shared__ float da[];  // [SA_DT][C]
+  const int d0 = blockIdx.x * SA_DT, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // softmax backward per row: da = w * (g - sum(g*w)), g = dwm * mask    (one warp per row, 2 rows per warp)
+  for (int dd = warp; dd < SA_DT; dd += 8) {
+    const int d = d0 + dd;
+    float dot = 0.f;
+    if (d < D1)
+      for (int c = lane; c < C; c += 32) dot += dwm[(size_t)d * C + c] * (mask ? mask[c] : 1.f) * w_soft[(size_t)d * C + c];
+    dot = warp_sum(dot);
+    for (int c = lane; c < C; c += 32) {
+      float v = 0.f;
+      if (d < D1) v = w_soft[(size_t)d * C + c] * (dwm[(size_t)d * C + c] * (mask ? mask[c] : 1.f) - dot);
+      da[dd * C + c] = v;
     }
-    if (c < C) { re0 = fmaf(da[c], cr[c], re0); im0 = fmaf(da[c], sr[c], im0); }
-    *reinterpret_cast<float2*>(dz_ri + ((size_t)d * K2 + m) * 2) = make_float2(re0 + re1, im0 + im1);
   }
+  __syncthreads();
+  const int m = blockIdx.y * 256 + tid;
+  if (m >= K2) return;
+  float re[SA_DT], im[SA_DT];
+#pragma unroll
+  for (int i = 0; i < SA_DT; ++i) re[i] = im[i] = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float cv = cosT[(size_t)c * K2 + m], sv = sinT[(size_t)c * K2 + m];
+#pragma unroll
+    for (int i = 0; i < SA_DT; ++i) {
+      const float a = da[i * C + c];
+      re[i] = fmaf(a, cv, re[i]);
+      im[i] = fmaf(a, sv, im[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < SA_DT; ++i)
+    if (d0 + i < D1) *reinterpret_cast<float2*>(dz_ri + ((size_t)(d0 + i) * K2 + m) * 2) = make_float2(re[i], im[i]);
 }
 
 }  // namespace sd
@@ -135,25 +150,30 @@ using namespace sd;
 extern "C" {
 
 int sd_sa_weights_fwd(const float* z_ri, const float* cos_t, const float* sin_t, const float* mask, float* w_soft,
-                      void* w_packed, int D1, int K2, int C, int D1p, int Cp, int dtype, void* stream) {
-  size_t smem = (size_t)(2 * K2 + ((C + 1) & ~1)) * sizeof(float) + (size_t)8 * C * sizeof(double);
-  SD_REQUIRE(smem <= 200 * 1024, "sd_sa_weights_fwd: K^2/C too large for shared memory");
-  if (dtype == SD_F32) {
-    if (smem > 48 * 1024) SD_CUDA(cudaFuncSetAttribute(sa_weights_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sa_weights_fwd_kernel<float><<<D1p, 256, smem, (cudaStream_t)stream>>>(z_ri, cos_t, sin_t, mask, w_soft, (float*)w_packed, D1, K2, C, Cp);
-  } else if (dtype == SD_BF16) {
-    if (smem > 48 * 1024) SD_CUDA(cudaFuncSetAttribute(sa_weights_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sa_weights_fwd_kernel<__nv_bfloat16><<<D1p, 256, smem, (cudaStream_t)stream>>>(z_ri, cos_t, sin_t, mask, w_soft, (__nv_bfloat16*)w_packed, D1, K2, C, Cp);
-  } else {
+                      void* w_packed, float* scratch, int D1, int K2, int C, int D1p, int Cp, int dtype, void* stream) {
+  const int mparts = SD_SA_MPARTS;
+  SD_REQUIRE(scratch != nullptr, "sd_sa_weights_fwd: scratch (SD_SA_MPARTS*D1*C floats) is null");
+  SD_REQUIRE((size_t)C * sizeof(float) <= 48 * 1024, "sd_sa_weights_fwd: too many sensors");
+  cudaStream_t st = (cudaStream_t)stream;
+  sa_logits_kernel<<<dim3(cdiv(D1, SA_DT), mparts), 256, 0, st>>>(z_ri, cos_t, sin_t, scratch, D1, K2, C, mparts);
+  if (check_launch("sa_logits")) return 1;
+  if (dtype == SD_F32)
+    sa_softmax_kernel<float><<<D1p, 256, C * sizeof(float), st>>>(scratch, mask, w_soft, (float*)w_packed, D1, C, Cp, mparts);
+  else if (dtype == SD_BF16)
+    sa_softmax_kernel<__nv_bfloat16><<<D1p, 256, C * sizeof(float), st>>>(scratch, mask, w_soft, (__nv_bfloat16*)w_packed, D1, C, Cp, mparts);
+  else {
     set_error("sd_sa_weights_fwd: bad dtype");
     return 1;
   }
-  return check_launch("sa_weights_fwd");
+  return check_launch("sa_softmax");
 }
 
-int sd_sa_weights_bwd(const float* dwm, const float* w_soft, const float* mask, const float* cos_t,
-                      const float* sin_t, float* dz_ri, int D1, int K2, int C, void* stream) {
-  sa_weights_bwd_kernel<<<dim3(D1, (K2 + 255) / 256 < 4 ? (K2 + 255) / 256 : 4), 256, C * sizeof(float), (cudaStream_t)stream>>>(dwm, w_soft, mask, cos_t, sin_t, dz_ri, K2, C);
+int sd_sa_weights_bwd(const float* dwm, const float* w_soft, const float* mask, const float* cos_T, const float* sin_T,
+                      float* dz_ri, int D1, int K2, int C, void* stream) {
+  const size_t smem = (size_t)SA_DT * C * sizeof(float);
+  SD_REQUIRE(smem <= 48 * 1024, "sd_sa_weights_bwd: too many sensors");
+  sa_weights_bwd_kernel<<<dim3(cdiv(D1, SA_DT), cdiv(K2, 256)), 256, smem, (cudaStream_t)stream>>>(dwm, w_soft, mask, cos_T, sin_T,
+                                                                                                  dz_ri, D1, K2, C);
   return check_launch("sa_weights_bwd");
 }
 

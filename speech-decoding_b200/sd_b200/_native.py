@@ -45,8 +45,8 @@ SIGNATURES = {
     "sd_nct_to_btc": [vp, vp, i32, i32, i32, i32, i32, vp],
     "sd_btc_to_nct": [vp, vp, i32, i32, i32, i32, i32, vp],
     "sd_pack_weight": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
-    "sd_pack_weights": [vp, i32, vp],
-    "sd_sa_weights_fwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
+    "sd_pack_weights": [vp, i32, i32, vp],
+    "sd_sa_weights_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "sd_sa_weights_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "sd_conv_fwd": [C.POINTER(ConvArgs), vp],
     "sd_conv_wgrad": [C.POINTER(WgradArgs), vp],

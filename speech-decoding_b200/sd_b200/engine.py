@@ -61,8 +61,9 @@ class WeightPack:
             raw = np.frombuffer(ctypes.string_at(ctypes.addressof(arr), ctypes.sizeof(arr)), dtype=np.uint8).copy()
             self._table = torch.from_numpy(raw).to(device)
             self._n = len(entries)
+            self._max_tiles = max(((e.Np + 31) // 32) * ((e.Kp + 31) // 32) for e in entries)
             self._sig = sig
-        nat.call("sd_pack_weights", self._table.data_ptr(), self._n, ops._st())
+        nat.call("sd_pack_weights", self._table.data_ptr(), self._n, self._max_tiles, ops._st())
 
     def wf(self, name):
         return self.bufs[name][0]
@@ -167,7 +168,11 @@ class SpatialAttentionStage(Stage):
         dwm = torch.zeros((D1, C), dtype=torch.float32, device=dout.device)
         ops.conv_wgrad(dout, sv["Xt"], dwm, K=C, N=D1, strides=(0, C, 1, 0))
         dz = run.gpool.view(m.z)
-        ops.sa_weights_bwd(dwm, sv["w_soft"], sv["mask"], m.cos, m.sin, K2, out=dz)
+        tt = getattr(m, "_sd_tables_T", None)          # transposed tables, cached (they are constant buffers)
+        if tt is None or tt[0].data_ptr() != m.cos.data_ptr():
+            tt = (m.cos, m.cos.t().contiguous(), m.sin.t().contiguous())
+            m._sd_tables_T = tt
+        ops.sa_weights_bwd(dwm, sv["w_soft"], sv["mask"], tt[1], tt[2], K2, out=dz)
         grads[m.z] = torch.view_as_complex(dz)
         return None
 

@@ -175,15 +175,17 @@ def sa_weights_fwd(z_ri, cos, sin, mask, D1, K2, C, dtype):
     D1p, Cp = rup8(D1), rup8(C)
     w_soft = torch.empty((D1, C), dtype=torch.float32, device=z_ri.device)
     w_packed = torch.empty((1, 1, D1p, Cp), dtype=dtype, device=z_ri.device)
-    nat.call("sd_sa_weights_fwd", _p(z_ri), _p(cos), _p(sin), _p(mask), _p(w_soft), _p(w_packed),
+    scratch = torch.empty((8, D1, C), dtype=torch.float32, device=z_ri.device)      # SD_SA_MPARTS partial logits
+    nat.call("sd_sa_weights_fwd", _p(z_ri), _p(cos), _p(sin), _p(mask), _p(w_soft), _p(w_packed), _p(scratch),
              D1, K2, C, D1p, Cp, code_of(w_packed), _st())
     return w_soft, w_packed
 
 
-def sa_weights_bwd(dwm, w_soft, mask, cos, sin, K2, out=None):
+def sa_weights_bwd(dwm, w_soft, mask, cos_T, sin_T, K2, out=None):
+    """cos_T, sin_T: the (C, K^2) transposes of the module's cos/sin buffers"""
     D1, C = w_soft.shape
     dz = out if out is not None else torch.empty((D1, K2, 2), dtype=torch.float32, device=dwm.device)
-    nat.call("sd_sa_weights_bwd", _p(dwm), _p(w_soft), _p(mask), _p(cos), _p(sin), _p(dz), D1, K2, C, _st())
+    nat.call("sd_sa_weights_bwd", _p(dwm), _p(w_soft), _p(mask), _p(cos_T), _p(sin_T), _p(dz), D1, K2, C, _st())
     return dz
 
 

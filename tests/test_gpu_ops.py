@@ -255,7 +255,7 @@ def test_spatial_attention_weights_fwd_bwd():
     assert rel(w_soft, w.detach()) < 1e-5
     assert rel(w_packed[0, 0, :D1, :Cc], wm.detach()) < 1e-5
     assert float(w_packed[0, 0, D1:].abs().max()) == 0 and float(w_packed[0, 0, :, Cc:].abs().max()) == 0
-    dz = ops.sa_weights_bwd(dwm.to(DEV), w_soft, mask.to(DEV), cos.to(DEV), sin.to(DEV), K * K)
+    dz = ops.sa_weights_bwd(dwm.to(DEV), w_soft, mask.to(DEV), cos.to(DEV).t().contiguous(), sin.to(DEV).t().contiguous(), K * K)
     assert rel(dz, torch.view_as_real(z.grad)) < 1e-4
 
 
