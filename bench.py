@@ -166,9 +166,10 @@ def run_ours(a, rank, world, local_rank):
     enc = BrainEncoder(args).to(dev).train()
     crit = CLIPLoss(args).to(dev).train()
     opt = torch.optim.Adam(list(enc.parameters()) + list(crit.parameters()), lr=3e-4)
+    dp = None
     if world > 1:
         from sd_b200.dist import DataParallel
-        DataParallel(enc, crit, sync_bn=bool(a.sync_bn))
+        dp = DataParallel(enc, crit, sync_bn=bool(a.sync_bn))
     B = a.batch
     Xh, Yh, ids = synth(B, 1000 + rank, pin=True)
     X, Y = Xh.to(dev), Yh.to(dev)
@@ -179,6 +180,8 @@ def run_ours(a, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def hot_step():
+        if dp is not None:
+            dp.prefetch_targets(Y)          # Y all-gather overlaps the encoder forward
         Z = enc(X, ids)
         loss = crit(Y, Z)
         for p in opt.param_groups[0]["params"]:
@@ -272,6 +275,8 @@ def run_ours(a, rank, world, local_rank):
                 prefetch(cur ^ 1)
             torch.cuda.current_stream().wait_event(evs[cur])
             Xd, Yd = bufs[cur]
+            if dp is not None:
+                dp.prefetch_targets(Yd)
             Z = enc(Xd, ids)
             loss = crit(Yd, Z)
             opt.zero_grad(set_to_none=True)

@@ -112,6 +112,22 @@ class DataParallel:
         pipe.bn_group = self.group if sync_bn else None
         pipe.host_group = self.host_group
         loss_fn.process_group = self.group
-        self.temp_reducer = loss_fn
+        self.loss_fn = loss_fn
+        loss_fn._prefetched = None
+
+    def prefetch_targets(self, Y):
+        """Start the all-gather of the speech embeddings for the coming step NOW (they are input data, known
+        before the encoder runs), so the transfer over NVLink overlaps the encoder forward instead of sitting
+        between the encoder and the loss.  Call right before `encoder(X, ids)`; `loss_fn(Y, Z)` with the same
+        Y then picks the gathered tensor up.  Optional: without it the loss gathers synchronously."""
+        world, _ = world_rank(self.group)
+        if world == 1:
+            return
+        y2 = Y.reshape(Y.shape[0], -1)
+        if y2.dtype != torch.float32 or not y2.is_contiguous():
+            y2 = y2.float().contiguous()
+        out = torch.empty((world * y2.shape[0], y2.shape[1]), dtype=y2.dtype, device=y2.device)
+        work = dist.all_gather_into_tensor(out, y2, group=self.group, async_op=True)
+        self.loss_fn._prefetched = (Y.data_ptr(), tuple(Y.shape), work, out, y2)
         # the temperature gradient is a partial sum per rank: the loss Function already
         # all-reduces `partial`, so dtemp is global -- nothing more to do for it.

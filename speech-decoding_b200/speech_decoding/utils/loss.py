@@ -99,6 +99,7 @@ class CLIPLoss(nn.Module):
         self._criterion = nn.CrossEntropyLoss(reduction=args.reduction)
         self.temp = nn.Parameter(torch.tensor([float(args.init_temperature)]))
         self.process_group = None
+        self._prefetched = None
 
     def forward(self, x, y, fast=True, return_logits=False):
         batch_size = x.size(0)
@@ -111,7 +112,13 @@ class CLIPLoss(nn.Module):
         yf = y.reshape(batch_size, -1).float().contiguous()
         group = self.process_group
         if group is not None:
-            xf = sd_dist.all_gather_rows(xf, group)
+            pre = getattr(self, "_prefetched", None)
+            self._prefetched = None
+            if pre is not None and pre[0] == x.data_ptr() and pre[1] == tuple(x.shape):
+                pre[2].wait()                    # gather launched before the encoder forward (DataParallel.prefetch_targets)
+                xf = pre[3]
+            else:
+                xf = sd_dist.all_gather_rows(xf, group)
         zn2 = getattr(y, "_sd_norm2", None)      # set by BrainEncoder.forward (fused into its last epilogue)
         if zn2 is not None and (zn2.shape[0] != batch_size or y.dtype != torch.float32):
             zn2 = None
