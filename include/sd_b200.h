@@ -139,7 +139,8 @@ int sd_bn_finalize(const double* stats, int C, int Cp, int64_t n, const float* g
                    float eps, int training, float* ss, void* stream);
 /* u = gelu(y*scale + shift) */
 int sd_bn_gelu_fwd(const void* y, const float* ss, void* u, int64_t rows, int Cp, int dtype, void* stream);
-/* with g = du * gelu'(y*scale+shift) (not stored): red (2,Cp) += sum g, sum g*xhat */
+/* with g = du * gelu'(y*scale+shift) (not stored): red (2,Cp) += sum g, sum g*y
+ * (sum g*xhat = invstd*(sum g*y - mean*sum g) is formed in fp64 by sd_bn_bwd_apply) */
 int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* red, int64_t rows, int Cp,
                           int dtype, void* stream);
 /* dy = scale*(g - sum_g/n - xhat*sum_gx/n), g recomputed from du and y, written in place over du;

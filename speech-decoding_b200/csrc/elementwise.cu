@@ -142,13 +142,13 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
 }
 __device__ __forceinline__ F8 ldp8(const float* p) { return ld8<float>(p); }
 
-constexpr int RED_ROWS = 128;   // rows per block, reduction kernels (fewer blocks => fewer atomics)
+constexpr int RED_ROWS = 96;   // rows per block, reduction kernels (fewer blocks => fewer atomics)
 constexpr int EW_ROWS = 64;     // rows per block, pure elementwise channel kernels
 
 // MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce over g = du * gelu'(bn(y)) (g is not stored:
 // the apply pass recomputes it, which is cheaper than a 59 MB write + read)
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3)
+__global__ void __launch_bounds__(256, 4)
 colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ ss, double* __restrict__ out,
                  int64_t rows, int Cp) {
   extern __shared__ float red_smem[];   // [blockDim.y][Cp] x 2
@@ -159,8 +159,8 @@ colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __rest
   F8 a, q;
 #pragma unroll
   for (int i = 0; i < 8; ++i) a.v[i] = q.v[i] = 0.f;
-  F8 sc, sh, mu, is;
-  if (MODE == 1) { sc = ldp8(ss + c); sh = ldp8(ss + Cp + c); mu = ldp8(ss + 2 * Cp + c); is = ldp8(ss + 3 * Cp + c); }
+  F8 sc, sh;
+  if (MODE == 1) { sc = ldp8(ss + c); sh = ldp8(ss + Cp + c); }
   for (int64_t r = r0 + ry; r < r1; r += UNR * R) {
     F8 v[UNR], yy[UNR];
 #pragma unroll
@@ -183,7 +183,7 @@ colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __rest
         for (int i = 0; i < 8; ++i) {
           float g = v[u].v[i] * gelu_grad_t<T>(fmaf(yy[u].v[i], sc.v[i], sh.v[i]));
           a.v[i] += g;
-          q.v[i] += g * (yy[u].v[i] - mu.v[i]) * is.v[i];
+          q.v[i] = fmaf(g, yy[u].v[i], q.v[i]);        // sum g*y; sum g*xhat = invstd*(sum g*y - mean*sum g) is formed in fp64 later
         }
       }
     }
@@ -319,7 +319,7 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
     const int tid = ry * blockDim.x + threadIdx.x;
     for (int ch = tid; ch < C; ch += blockDim.x * R) {
       if (dbeta) dbeta[ch] = (float)red[ch] * dscale;
-      if (dgamma) dgamma[ch] = (float)red[Cp + ch] * dscale;
+      if (dgamma) dgamma[ch] = (float)(((double)ss[3 * Cp + ch]) * (red[Cp + ch] - (double)ss[2 * Cp + ch] * red[ch])) * dscale;
     }
   }
   const F8 sc = ldp8(ss + c), sh = ldp8(ss + Cp + c), mu = ldp8(ss + 2 * Cp + c), is = ldp8(ss + 3 * Cp + c);
@@ -328,7 +328,8 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
   F8 k2, k3;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float sg = (float)red[c + i] * invn, sx = (float)red[Cp + c + i] * invn;
+    const float sg = (float)red[c + i] * invn;
+    const float sx = (float)((double)is.v[i] * (red[Cp + c + i] - (double)mu.v[i] * red[c + i])) * invn;   // sum g*xhat / n
     k2.v[i] = training ? -sc.v[i] * is.v[i] * sx : 0.f;
     k3.v[i] = training ? sc.v[i] * (mu.v[i] * is.v[i] * sx - sg) : 0.f;
   }

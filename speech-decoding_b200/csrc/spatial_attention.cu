@@ -22,7 +22,7 @@ constexpr int SA_MC = 128;    // frequencies per shared-memory chunk
 __global__ void __launch_bounds__(256)
 sa_logits_kernel(const float* __restrict__ z_ri, const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                  float* __restrict__ part, int D1, int K2, int C, int mparts) {
-  __shared__ float zs[SA_DT][2 * SA_MC];
+  __shared__ __align__(16) float zs[SA_MC][2 * SA_DT];   // [m][d] (re,im) pairs: one frequency = 8 LDS.128
   const int d0 = blockIdx.x * SA_DT, mp = blockIdx.y, tid = threadIdx.x;
   const int m_lo = (int)((long long)K2 * mp / mparts), m_hi = (int)((long long)K2 * (mp + 1) / mparts);
   for (int c0 = 0; c0 < C; c0 += 256) {
@@ -34,15 +34,20 @@ sa_logits_kernel(const float* __restrict__ z_ri, const float* __restrict__ cos_t
       const int mn = min(SA_MC, m_hi - mc);
       __syncthreads();
       for (int i = tid; i < SA_DT * 2 * mn; i += 256) {
-        const int dd = i / (2 * mn), r = i % (2 * mn);
-        zs[dd][r] = (d0 + dd < D1) ? z_ri[((size_t)(d0 + dd) * K2 + mc) * 2 + r] : 0.f;
+        const int dd = i / (2 * mn), r = i % (2 * mn);       // r = 2*m + {re,im}: coalesced global read
+        zs[r >> 1][2 * dd + (r & 1)] = (d0 + dd < D1) ? z_ri[((size_t)(d0 + dd) * K2 + mc) * 2 + r] : 0.f;
       }
       __syncthreads();
       if (c < C) {
         for (int m = 0; m < mn; ++m) {
           const float cv = cos_t[(size_t)(mc + m) * C + c], sv = sin_t[(size_t)(mc + m) * C + c];
+          const float4* zr = reinterpret_cast<const float4*>(&zs[m][0]);
 #pragma unroll
-          for (int i = 0; i < SA_DT; ++i) acc[i] = fmaf(zs[i][2 * m], cv, fmaf(zs[i][2 * m + 1], sv, acc[i]));
+          for (int i = 0; i < SA_DT / 2; ++i) {
+            const float4 q = zr[i];                          // (re,im) of rows 2i and 2i+1
+            acc[2 * i] = fmaf(q.x, cv, fmaf(q.y, sv, acc[2 * i]));
+            acc[2 * i + 1] = fmaf(q.z, cv, fmaf(q.w, sv, acc[2 * i + 1]));
+          }
         }
       }
     }
