@@ -344,7 +344,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       }
       long long e0 = clock64();
-      mbar_wait(tfull_bar(acc), acc_ph);
+      mbar_wait_relaxed(tfull_bar(acc), acc_ph);
       tc_fence_after();
       if (p.res) {
         mbar_wait(res_bar(ew), res_ph);

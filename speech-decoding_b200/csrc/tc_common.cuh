@@ -79,6 +79,27 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Long waits (epilogue warps waiting for a whole tile of MMAs): back off with nanosleep so that the pollers do
+// not compete with the producer / MMA warps for issue slots and the shared-memory barrier unit.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint32_t spin = 0;; ++spin) {
+    __nanosleep(128);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spin & 0x3ff) == 0x3ff) {
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) {
+        printf("sd_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+
 // ---- device: TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

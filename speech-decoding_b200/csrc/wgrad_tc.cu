@@ -154,7 +154,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     const int n = n0 + quad * 32 + lane;
     const int nch = p.block_c >> 4;
     const int ch0 = hsel ? (nch + 1) / 2 : 0, ch1 = hsel ? nch : (nch + 1) / 2;
-    mbar_wait(tfull_bar, 0);
+    mbar_wait_relaxed(tfull_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     float* dwn = p.dw + (long long)g * p.gs + (long long)n * p.sn + (long long)j * p.sj;
@@ -321,7 +321,7 @@ conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     const int n = n0 + quad * 32 + lane;
     const int nch = p.block_c >> 4;
     const int ch0 = hsel ? (nch + 1) / 2 : 0, ch1 = hsel ? nch : (nch + 1) / 2;
-    mbar_wait(tfull_bar, 0);
+    mbar_wait_relaxed(tfull_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     float* dwn = p.dw + (long long)g * p.gs + (long long)n * p.sn;
