@@ -44,6 +44,8 @@ extern "C" {
 #define SD_IMPL_AUTO 0
 #define SD_IMPL_SIMT 1 /* fp32-accumulate CUDA-core kernels (any dtype)                                */
 #define SD_IMPL_TC 2   /* tcgen05/TMEM/TMA kernels (bf16)                                              */
+#define SD_IMPL_TC_1CTA 3 /* SD_IMPL_TC without CTA-pair (cta_group::2) tiles: tests compare the variants   */
+#define SD_IMPL_TC_WS 4   /* SD_IMPL_TC with weight-stationary CTA-pair tiles (experimental, not the default)  */
 
 const char* sd_last_error(void);
 int sd_abi_version(void);

@@ -48,8 +48,9 @@ int sd_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int sd_set_impl(int impl) {
-  SD_REQUIRE(impl >= SD_IMPL_AUTO && impl <= SD_IMPL_TC, "sd_set_impl: bad value %d", impl);
-  g_impl = impl;
+  SD_REQUIRE(impl >= SD_IMPL_AUTO && impl <= SD_IMPL_TC_WS, "sd_set_impl: bad value %d", impl);
+  g_impl = impl >= SD_IMPL_TC_1CTA ? SD_IMPL_TC : impl;
+  if (impl != SD_IMPL_SIMT) set_conv_pair(impl == SD_IMPL_TC_1CTA ? 0 : impl == SD_IMPL_AUTO ? 1 : 2, impl == SD_IMPL_TC_WS);
   return 0;
 }
 

@@ -27,6 +27,13 @@ namespace sd {
 
 using namespace tc;
 
+// make TIMELINE=1: per-role clock64 accounting printed by the first CTA (pair) -- tools only, never shipped on
+#ifdef SD_TIMELINE
+#define TL(...) __VA_ARGS__
+#else
+#define TL(...)
+#endif
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -52,7 +59,7 @@ struct FwdParams {
   int block_n, n_tiles, m_tiles_per_sample, num_tiles, k_blocks;
   int act, out_mode, D2, Op;
   // shared-memory plan (byte offsets from the 1024-aligned base)
-  int dbg, sa_slots, sw_slots, a_bytes, w_bytes, a_rows, halo, off_w, w0cols, off_stg0, off_stg1, off_bias, off_stats, off_bar, cols_alloc;
+  int num_mpairs, sa_slots, sw_slots, a_bytes, w_bytes, a_rows, halo, off_w, w0cols, off_stg0, off_stg1, off_stgr, off_bias, off_stats, off_bar, cols_alloc;
 };
 
 // tensor maps of the epilogue tensors, one per column-half of the tile (the halves may differ in width)
@@ -141,6 +148,12 @@ __device__ __forceinline__ void lds16_f32_add(uint32_t saddr, float (&v)[16]) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
 
+// PAIR: the two CTAs of a cluster work on two consecutive 128-row tiles of the SAME column tile as one
+// M=256 tcgen05.mma.cta_group::2: each CTA loads its own activation tile and only HALF of the weight tile
+// (block_n/2 rows), which halves the dominant L2->SM operand stream.  The leader (rank 0) issues the MMAs and
+// owns the full / accumulator-empty barriers; commits are multicast to both CTAs; each CTA runs its own epilogue
+// on its own 128 TMEM lanes.
+template <bool PAIR, bool WS, int TAPS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ EpiMaps em, const FwdParams p) {
@@ -162,15 +175,34 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool glu = p.act == SD_ACT_GLU;
   const int half_n = p.block_n >> 1;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  // Tile walk.  Streaming: tile = (row tile [pair], column tile), column tile fastest, strided over the CTAs
+  // [pairs].  Weight-stationary (ws): the pair owns column tile `n_fixed` for the whole kernel and `tile` walks the
+  // row-tile pairs, strided over the pairs that own the same column tile.
+  constexpr bool ws = WS;
+  static_assert(PAIR || !WS, "weight-stationary tiles are CTA-pair tiles");
+  int tile_begin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  int tile_end = p.num_tiles, n_fixed = 0;
+  if (ws) {
+    n_fixed = tile_begin % p.n_tiles;
+    tile_begin = tile_begin / p.n_tiles;
+    tile_step = (tile_step - n_fixed + p.n_tiles - 1) / p.n_tiles;
+    tile_end = p.num_mpairs;
+  }
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
     for (int s = 0; s < p.sa_slots; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
-    for (int s = 0; s < p.sw_slots; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
+    if (ws) {   // one single-use "resident weights of k-block kb have landed" barrier per k-block
+      for (int s = 0; s < p.k_blocks; ++s) mbar_init(wfull_bar(s), 1);
+    } else {
+      for (int s = 0; s < p.sw_slots; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), NUM_EPI_WARPS);
+      mbar_init(tempty_bar(a), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
     }
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
     fence_barrier_init();
@@ -188,11 +220,15 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
     if (p.stats)
-      for (int i = threadIdx.x; i < 2 * p.cols_alloc; i += NUM_THREADS) s_stats[i] = 0.f;
+      for (int i = threadIdx.x; i < 8 * p.cols_alloc; i += NUM_THREADS) s_stats[i] = 0.f;   // [quadrant][sum, sumsq][col]
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
@@ -207,86 +243,142 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
     int sa = 0, sw = 0;
     uint32_t pha = 0, phw = 0;
-    const uint32_t a_tx = (uint32_t)p.a_rows * 128u, w_tx = (uint32_t)p.block_n * BLOCK_K * 2;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
-      const int b = m_idx / p.m_tiles_per_sample;
+    const uint32_t a_tx = (uint32_t)p.a_rows * 128u, w_tx = (uint32_t)p.block_n * BLOCK_K * 2;   // per pair if PAIR
+    TL(long long tl_t0 = clock64(), tl_ae = 0, tl_we = 0, tl_q;)
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      const int m_tile = ws ? tile : tile / p.n_tiles, n_idx = ws ? n_fixed : tile % p.n_tiles;
+      const int m_idx = PAIR ? 2 * m_tile + rank : m_tile;
+      const int b = m_idx / p.m_tiles_per_sample;   // PAIR: may be == B for the odd tile out (TMA zero-fills it)
       const int t0 = (m_idx % p.m_tiles_per_sample) * BLOCK_M;
-      const int g = p.widx ? __ldg(p.widx + b) : 0;
+      const int g = p.widx ? __ldg(p.widx + b) : 0;  // (never PAIR: the pair shares one weight tile)
       const int row0 = glu ? n_idx * half_n : n_idx * p.block_n;
       const int row1 = glu ? p.D2 + n_idx * half_n : row0 + half_n;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
+        TL(tl_q = clock64();)
         mbar_wait(aempty_bar(sa), pha ^ 1);
+        TL(tl_ae += clock64() - tl_q;)
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(afull_bar(sa), a_tx);
-          tma_load_3d(smem_base + sa * p.a_bytes, &tmap_a, afull_bar(sa), kb * BLOCK_K, t0 - p.halo, b);
+          if (PAIR) {
+            if (rank == 0) mbar_arrive_expect_tx(afull_bar(sa), 2 * a_tx);
+            tma_load_3d_pair(smem_base + sa * p.a_bytes, &tmap_a, mapa_cluster(afull_bar(sa), 0), kb * BLOCK_K, t0 - p.halo, b);
+          } else {
+            mbar_arrive_expect_tx(afull_bar(sa), a_tx);
+            tma_load_3d(smem_base + sa * p.a_bytes, &tmap_a, afull_bar(sa), kb * BLOCK_K, t0 - p.halo, b);
+          }
         }
         __syncwarp();
         if (++sa == p.sa_slots) { sa = 0; pha ^= 1; }
-        for (int j = 0; j < p.taps; ++j) {
+        if (ws) {   // resident weights: loaded once, while the first row tile streams in
+          if (tile == tile_begin && elect_one_sync()) {
+            if (rank == 0) mbar_arrive_expect_tx(wfull_bar(kb), (uint32_t)TAPS * w_tx);
+            for (int j = 0; j < TAPS; ++j)
+              tma_load_3d_pair(smem_base + p.off_w + (kb * TAPS + j) * p.w_bytes, &tmap_w, mapa_cluster(wfull_bar(kb), 0),
+                               kb * BLOCK_K, rank ? row1 : row0, j);
+          }
+          __syncwarp();
+          continue;
+        }
+        for (int j = 0; j < TAPS; ++j) {
+          TL(tl_q = clock64();)
           mbar_wait(wempty_bar(sw), phw ^ 1);
+          TL(tl_we += clock64() - tl_q;)
           if (elect_one_sync()) {
             const uint32_t sb = smem_base + p.off_w + sw * p.w_bytes;
-            mbar_arrive_expect_tx(wfull_bar(sw), w_tx);
-            tma_load_3d(sb, &tmap_w, wfull_bar(sw), kb * BLOCK_K, row0, g * p.taps + j);
-            tma_load_3d(sb + half_n * (BLOCK_K * 2), &tmap_w, wfull_bar(sw), kb * BLOCK_K, row1, g * p.taps + j);
+            if (PAIR) {   // this CTA's half of the rows only
+              if (rank == 0) mbar_arrive_expect_tx(wfull_bar(sw), w_tx);
+              tma_load_3d_pair(sb, &tmap_w, mapa_cluster(wfull_bar(sw), 0), kb * BLOCK_K, rank ? row1 : row0, g * TAPS + j);
+            } else {
+              mbar_arrive_expect_tx(wfull_bar(sw), w_tx);
+              tma_load_3d(sb, &tmap_w, wfull_bar(sw), kb * BLOCK_K, row0, g * TAPS + j);
+              tma_load_3d(sb + half_n * (BLOCK_K * 2), &tmap_w, wfull_bar(sw), kb * BLOCK_K, row1, g * TAPS + j);
+            }
           }
           __syncwarp();
           if (++sw == p.sw_slots) { sw = 0; phw ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+    TL(if (lane == 0 && blockIdx.x < 2) printf("blk %d producer: total %lld | wait a-empty %lld w-empty %lld\n", (int)blockIdx.x,
+                                               clock64() - tl_t0, tl_ae, tl_we);)
+  } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (whole warp, one elected lane issues) =====================
-    const uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, BLOCK_M, (uint32_t)p.block_n);
+    const uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, PAIR ? 2 * BLOCK_M : BLOCK_M, (uint32_t)p.block_n);
     const uint32_t dhi = smem_desc_hi(1024);
     const uint32_t tap_step = (uint32_t)(p.halo * 128) >> 4;   // descriptor units per tap (taps==3: halo == dil)
     int sa = 0, sw = 0;
     uint32_t pha = 0, phw = 0;
     int it_tile = 0;
-    long long d_te = 0, d_af = 0, d_wf = 0, d_is = 0, d_t0 = clock64();
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
+    TL(long long tl_t0 = clock64(), tl_te = 0, tl_af = 0, tl_wf = 0, tl_q;)
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it_tile) {
       const int acc = it_tile & 1;
       const uint32_t acc_ph = (it_tile >> 1) & 1;
-      long long q0 = clock64();
+      TL(tl_q = clock64();)
       mbar_wait(tempty_bar(acc), acc_ph ^ 1);
       tc_fence_after();
-      d_te += clock64() - q0;
+      TL(tl_te += clock64() - tl_q;)
       const uint32_t d_tmem = tmem_base + acc * MAX_BLOCK_N;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
-        long long q1 = clock64();
+        TL(tl_q = clock64();)
         mbar_wait(afull_bar(sa), pha);
-        d_af += clock64() - q1;
+        TL(tl_af += clock64() - tl_q;)
         const uint32_t alo = smem_desc_lo(smem_base + sa * p.a_bytes, 16);
-        for (int j = 0; j < p.taps; ++j) {
-          long long q2 = clock64();
+        if constexpr (WS) {
+          // resident weights: one elected section issues all TAPS x 4 MMAs of the k-block back to back
+          if (it_tile == 0) mbar_wait(wfull_bar(kb), 0);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t blo0 = smem_desc_lo(smem_base + p.off_w + kb * TAPS * p.w_bytes, 16);
+            const uint32_t w_step = (uint32_t)p.w_bytes >> 4;
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k)
+                umma_f16_pair(d_tmem, desc64(alo + j * tap_step + 2 * k, dhi), desc64(blo0 + j * w_step + 2 * k, dhi), idesc,
+                              (kb | j | k) != 0);
+            }
+            umma_commit_pair(aempty_bar(sa));
+            if (kb == p.k_blocks - 1) umma_commit_pair(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++sa == p.sa_slots) { sa = 0; pha ^= 1; }
+          continue;
+        }
+        for (int j = 0; j < TAPS; ++j) {
+          TL(tl_q = clock64();)
           mbar_wait(wfull_bar(sw), phw);
           tc_fence_after();
-          long long q3 = clock64();
-          d_wf += q3 - q2;
+          TL(tl_wf += clock64() - tl_q;)
           if (elect_one_sync()) {
             const uint32_t blo = smem_desc_lo(smem_base + p.off_w + sw * p.w_bytes, 16);
             const uint32_t aj = alo + j * tap_step;
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k)   // +32 B per 16-element k-step inside the swizzled row
-              umma_f16(d_tmem, desc64(aj + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (kb | j | k) != 0);
-            umma_commit(wempty_bar(sw));
-            if (j == p.taps - 1) {
-              umma_commit(aempty_bar(sa));
-              if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
+            for (int k = 0; k < BLOCK_K / 16; ++k) {  // +32 B per 16-element k-step inside the swizzled row
+              if (PAIR) umma_f16_pair(d_tmem, desc64(aj + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (kb | j | k) != 0);
+              else umma_f16(d_tmem, desc64(aj + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (kb | j | k) != 0);
+            }
+            if (PAIR) {
+              umma_commit_pair(wempty_bar(sw));
+              if (j == TAPS - 1) {
+                umma_commit_pair(aempty_bar(sa));
+                if (kb == p.k_blocks - 1) umma_commit_pair(tfull_bar(acc));
+              }
+            } else {
+              umma_commit(wempty_bar(sw));
+              if (j == TAPS - 1) {
+                umma_commit(aempty_bar(sa));
+                if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
+              }
             }
           }
           __syncwarp();
-          d_is += clock64() - q3;
           if (++sw == p.sw_slots) { sw = 0; phw ^= 1; }
         }
         if (++sa == p.sa_slots) { sa = 0; pha ^= 1; }
       }
     }
-    if (p.dbg >= 2 && lane == 0 && (blockIdx.x % 49) == 0)
-      printf("blk %d mma: tiles %d total %lld | wait tmem-empty %lld a-full %lld w-full %lld | issue %lld (per k-block-tap %.0f)\n", (int)blockIdx.x,
-             it_tile, clock64() - d_t0, d_te, d_af, d_wf, d_is, (double)d_is / (it_tile * p.k_blocks * p.taps));
-  } else {
+    TL(if (lane == 0 && blockIdx.x < 2) printf("blk %d mma: tiles %d total %lld | wait acc-empty %lld a-full %lld w-full %lld | issue %lld\n", (int)blockIdx.x,
+                                               it_tile, clock64() - tl_t0, tl_te, tl_af, tl_wf, clock64() - tl_t0 - tl_te - tl_af - tl_wf);)
+  } else if (warp >= 2) {
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
@@ -308,50 +400,64 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t stg0 = quad0 + (glu ? 2 : 1) * (hsel ? 32 * p.w0cols * 2 : 0);
     const uint32_t stg0b = stg0 + box_bytes;                                     // GLU gate half
     const uint32_t stg1 = smem_base + p.off_stg1 + quad * (32 * (glu ? half_n : p.block_n) * 2) + (hsel ? 32 * p.w0cols * 2 : 0);
+    // residual tile of this warp: its own buffer, so that the NEXT tile's residual can be fetched a whole tile ahead
+    const uint32_t stgr = smem_base + p.off_stgr + quad * (32 * p.block_n * 2) + (hsel ? 32 * p.w0cols * 2 : 0);
     const uint32_t my0 = stg0 + lane * seg_bytes, my0b = stg0b + lane * seg_bytes, my1 = stg1 + lane * seg_bytes;
+    const uint32_t myr = stgr + lane * seg_bytes;
     const CUtensorMap* m_out = &em.out[hsel];
     const CUtensorMap* m_pre = &em.pre[hsel];
     const CUtensorMap* m_res = &em.res[hsel];
     const CUtensorMap* m_preb = &em.preb[hsel];
     uint32_t res_ph = 0;
-    long long d_ew = 0, d_ework = 0;
+    TL(long long tl_t0 = clock64(), tl_rd = 0, tl_tf = 0, tl_rs = 0, tl_ch = 0, tl_st = 0, tl_q, tl_r;)
+
+    // fetch this warp's residual tile of tile `tl` (non-GLU only)
+    auto fetch_residual = [&](const int tl) {
+      const int m_tile = ws ? tl : tl / p.n_tiles, n_idx = ws ? n_fixed : tl % p.n_tiles;
+      const int m_idx = PAIR ? 2 * m_tile + rank : m_tile;
+      const int b = m_idx / p.m_tiles_per_sample;
+      const int t_w = (m_idx % p.m_tiles_per_sample) * BLOCK_M + quad * 32;
+      const int c0 = n_idx * p.block_n + seg_col;
+      if (elect_one_sync()) {
+        if (seg_cols > 0 && t_w < p.T && b < p.B && c0 < p.Np) {
+          mbar_arrive_expect_tx(res_bar(ew), box_bytes);
+          tma_load_3d(stgr, m_res, res_bar(ew), c0, t_w, b);
+        } else {
+          mbar_arrive(res_bar(ew));
+        }
+      }
+      __syncwarp();
+    };
+    if (p.res && tile_begin < tile_end) fetch_residual(tile_begin);
 
     int it_tile = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it_tile) {
       const int acc = it_tile & 1;
       const uint32_t acc_ph = (it_tile >> 1) & 1;
-      const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
+      const int m_tile = ws ? tile : tile / p.n_tiles, n_idx = ws ? n_fixed : tile % p.n_tiles;
+      const int m_idx = PAIR ? 2 * m_tile + rank : m_tile;
       const int b = m_idx / p.m_tiles_per_sample;
       const int t_w = (m_idx % p.m_tiles_per_sample) * BLOCK_M + quad * 32;   // first row of this warp
       const int t = t_w + lane;
-      const bool valid = t < p.T;
+      const bool valid = t < p.T && b < p.B;
       const int n0 = glu ? n_idx * half_n : n_idx * p.block_n;  // first output channel of the tile
       const int lim = glu ? p.Op : p.Np;
       // does this warp's tile intersect the tensor at all?  (TMA clips partial overlap)
-      const bool live = seg_cols > 0 && t_w < p.T && n0 + seg_col < lim;
+      const bool live = seg_cols > 0 && t_w < p.T && b < p.B && n0 + seg_col < lim;
 
       // the previous tile's tensor stores must have finished reading the staging tiles
+      TL(tl_q = clock64();)
       if (elect_one_sync()) bulk_wait_read0();
       __syncwarp();
-      if (p.res) {
-        if (elect_one_sync()) {
-          if (live) {
-            mbar_arrive_expect_tx(res_bar(ew), box_bytes);
-            tma_load_3d(stg0, m_res, res_bar(ew), n0 + seg_col, t_w, b);
-          } else {
-            mbar_arrive(res_bar(ew));
-          }
-        }
-      }
-      long long e0 = clock64();
+      TL(tl_r = clock64(); tl_rd += tl_r - tl_q; tl_q = tl_r;)
       mbar_wait_relaxed(tfull_bar(acc), acc_ph);
       tc_fence_after();
+      TL(tl_r = clock64(); tl_tf += tl_r - tl_q; tl_q = tl_r;)
       if (p.res) {
         mbar_wait(res_bar(ew), res_ph);
         res_ph ^= 1;
       }
-      long long e1 = clock64();
-      d_ew += e1 - e0;
+      TL(tl_r = clock64(); tl_rs += tl_r - tl_q; tl_q = tl_r;)
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * MAX_BLOCK_N;
       float sumsq = 0.f;
       float* nct_row = p.out_nct + (size_t)b * p.N * p.T + (valid ? t : 0);
@@ -367,7 +473,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
           lds16_f32_add(s_bias + nb * 4, v);
-          if (p.res && live) lds16_bf16_add(my0 + so, v);
+          if (p.res && live) lds16_bf16_add(myr + so, v);
           if (p.act == SD_ACT_GELU) {
             if (p.preact) sts16_bf16(my0 + so, v);
 #pragma unroll
@@ -398,24 +504,48 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         fence_proxy_async();
         __syncwarp();
+        if (p.res && tile + tile_step < tile_end) fetch_residual(tile + tile_step);   // a whole tile ahead
+        TL(tl_r = clock64(); tl_ch += tl_r - tl_q; tl_q = tl_r;)
         if (p.stats && live) {
           // BatchNorm batch statistics of the values exactly as stored (bf16): column sums over this warp's
           // staged tile -- lane = column pair, conflict-free 4-byte reads down the rows
           const int rows_valid = min(32, p.T - t_w);
           for (int cp = lane; cp < (seg_cols >> 1); cp += 32) {
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            for (int r = 0; r < rows_valid; ++r) {
-              uint32_t w;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(stg0 + r * seg_bytes + cp * 4));
-              float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-              s0 += f.x; s1 += f.y;
-              q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+            const uint32_t col = stg0 + cp * 4;
+            if (rows_valid == 32) {   // 8 independent loads in flight, two accumulator chains
+              float s2 = 0.f, s3 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+              for (int r0 = 0; r0 < 32; r0 += 8) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[i]) : "r"(col + (r0 + i) * seg_bytes));
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                  float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                  float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i + 1]));
+                  s0 += f.x; s1 += f.y; s2 += g.x; s3 += g.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1); q2 = fmaf(g.x, g.x, q2); q3 = fmaf(g.y, g.y, q3);
+                }
+              }
+              s0 += s2; s1 += s3; q0 += q2; q1 += q3;
+            } else {
+              for (int r = 0; r < rows_valid; ++r) {
+                uint32_t w;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(col + r * seg_bytes));
+                float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+                s0 += f.x; s1 += f.y;
+                q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+              }
             }
-            const int n = n0 + seg_col + 2 * cp;
-            atomicAdd(s_stats + n, s0);
-            atomicAdd(s_stats + n + 1, s1);
-            atomicAdd(s_stats + p.cols_alloc + n, q0);
-            atomicAdd(s_stats + p.cols_alloc + n + 1, q1);
+            // this (quadrant, column pair) accumulator is touched by this lane only: plain read-modify-write
+            // (shared-memory float atomics are CAS spin loops and the four quadrants would collide on them)
+            float2* acc_s = reinterpret_cast<float2*>(s_stats + quad * 2 * p.cols_alloc + n0 + seg_col + 2 * cp);
+            float2* acc_q = reinterpret_cast<float2*>(s_stats + (quad * 2 + 1) * p.cols_alloc + n0 + seg_col + 2 * cp);
+            float2 a = *acc_s, q = *acc_q;
+            a.x += s0; a.y += s1; q.x += q0; q.y += q1;
+            *acc_s = a; *acc_q = q;
           }
         }
         if (elect_one_sync()) {
@@ -474,22 +604,31 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
       if (p.rownorm2) {
         sumsq = warp_sum(sumsq);
-        if (lane == 0) atomicAdd(p.rownorm2 + b, sumsq);
+        if (lane == 0 && b < p.B) atomicAdd(p.rownorm2 + b, sumsq);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      d_ework += clock64() - e1;
+      TL(tl_r = clock64(); tl_st += tl_r - tl_q; tl_q = tl_r;)
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
-    if (p.dbg >= 2 && threadIdx.x == 64 && (blockIdx.x % 49) == 0)
-      printf("blk %d epi: tiles %d wait-for-acc %lld work %lld (per tile %.0f)\n", (int)blockIdx.x, it_tile, d_ew, d_ework, (double)d_ework / it_tile);
     if (elect_one_sync()) bulk_wait0();
     __syncwarp();
+    TL(if (lane == 0 && blockIdx.x < 2 && (ew == 0 || ew == 7))
+         printf("blk %d epi warp %d: tiles %d total %lld | wait store-read %lld acc-full %lld residual %lld | chunks %lld stats+store %lld (non-GLU)\n",
+                (int)blockIdx.x, ew, it_tile, clock64() - tl_t0, tl_rd, tl_tf, tl_rs, tl_ch, tl_st);)
     if (p.stats) {
       epi_bar_sync();
       const int et = threadIdx.x - 64;
       for (int i = et; i < p.n_tiles * p.block_n && i < p.Np; i += NUM_EPI_WARPS * 32) {
-        float a = s_stats[i], q = s_stats[p.cols_alloc + i];
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          a += s_stats[w * 2 * p.cols_alloc + i];
+          q += s_stats[(w * 2 + 1) * p.cols_alloc + i];
+        }
         if (a != 0.f || q != 0.f) {
           atomicAdd(p.stats + i, (double)a);
           atomicAdd(p.stats + p.Np + i, (double)q);
@@ -499,8 +638,12 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (PAIR) cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other can still touch it
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // pick the N tile: multiple of `gran`, <= 256, minimal padded total, fewest tiles on ties
@@ -521,6 +664,9 @@ CUtensorMap ta_dummy() {
   memset(&m, 0, sizeof(m));
   return m;
 }
+
+int g_conv_ws = 0;   // weight-stationary pairs: measured slower than streaming pairs at the cfg2 shapes (narrower MMAs)
+int g_conv_pair = -1;   // -1: not decided yet (SD_B200_CONV_PAIR=0 disables the CTA-pair tiles)
 
 int sm_count() {
   static int n = 0;
@@ -568,6 +714,11 @@ int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint6
 
 }  // namespace tc
 
+void set_conv_pair(int on, bool ws) {   // on: 0 never, 1 where it pays (default), 2 wherever legal (tests)
+  g_conv_pair = on;
+  g_conv_ws = ws ? 1 : 0;
+}
+
 bool conv_fwd_tc_supported(const sd_conv_args& a) {
   if (a.dtype != SD_BF16) return false;
   if (a.act == SD_ACT_GLU && ((a.N / 2) % 8 != 0 || a.out_mode != SD_OUT_BTC || a.N % 2)) return false;
@@ -598,52 +749,100 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   p.act = a.act; p.out_mode = a.out_mode;
   p.D2 = glu ? a.N / 2 : 0;
   p.Op = glu ? (p.D2 + 7) / 8 * 8 : 0;
-  if (glu) {
-    p.block_n = pick_block_n(2 * p.Op, 32);   // value half and gate half: each a multiple of 16 columns
-    p.n_tiles = (p.Op + p.block_n / 2 - 1) / (p.block_n / 2);
-    p.cols_alloc = p.n_tiles * (p.block_n / 2);
-  } else {
-    p.block_n = pick_block_n(a.Np, 16);
-    p.n_tiles = (a.Np + p.block_n - 1) / p.block_n;
-    p.cols_alloc = p.n_tiles * p.block_n;
-  }
   p.m_tiles_per_sample = (a.T + BLOCK_M - 1) / BLOCK_M;
-  p.num_tiles = a.B * p.m_tiles_per_sample * p.n_tiles;
   p.k_blocks = (a.Kp + BLOCK_K - 1) / BLOCK_K;
-
-  // shared-memory plan
-  p.dbg = getenv("SD_DBG") ? atoi(getenv("SD_DBG")) : 0;
   p.halo = a.taps == 3 ? a.dil : 0;
   p.a_rows = BLOCK_M + 2 * p.halo;
   p.a_bytes = (p.a_rows * 128 + 1023) / 1024 * 1024;
-  p.w_bytes = p.block_n * BLOCK_K * 2;
-  const int nch = (glu ? p.block_n / 2 : p.block_n) / 16;
-  const int w0 = (nch + 1) / 2 * 16, w1 = nch / 2 * 16;          // column widths of the two warp halves
-  p.w0cols = w0;
-  const bool need_stg1 = glu || (a.act == SD_ACT_GELU && a.out_mode == SD_OUT_BTC);
-  const int stg_bytes = BLOCK_M * p.block_n * 2;
-  const int stg1_bytes = need_stg1 ? BLOCK_M * (glu ? p.block_n / 2 : p.block_n) * 2 : 0;
-  const int tail = stg_bytes + stg1_bytes + (glu ? 2 : 1) * p.cols_alloc * 4 + 2 * p.cols_alloc * 4 + 512;
-  const int ring = SMEM_LIMIT - 1024 - tail;
-  // taps==3: few activation slots (each feeds 3 weight tiles), the rest of the ring holds weight tiles
-  int sa = a.taps == 3 ? 3 : (ring / (p.a_bytes + p.w_bytes));
-  if (a.taps == 3 && ring - sa * p.a_bytes < 5 * p.w_bytes) sa = 2;
-  if (sa > MAX_A_SLOTS) sa = MAX_A_SLOTS;
-  int sw = (ring - sa * p.a_bytes) / p.w_bytes;
-  if (sw > MAX_W_SLOTS) sw = MAX_W_SLOTS;
-  if (a.taps == 3 && sw > 3 * sa + 3) sw = 3 * sa + 3;
-  SD_REQUIRE(sa >= 1 && sw >= 2 && p.a_rows <= 256, "conv_fwd_tc: operand rings do not fit (block_n=%d dil=%d)", p.block_n, a.dil);
-  p.sa_slots = sa; p.sw_slots = sw;
-  p.off_w = sa * p.a_bytes;
-  int off = p.off_w + sw * p.w_bytes;
-  p.off_stg0 = off; off += stg_bytes;
-  p.off_stg1 = off; off += stg1_bytes;
-  p.off_bias = off; off += (glu ? 2 : 1) * p.cols_alloc * 4;
-  p.off_stats = off; off += 2 * p.cols_alloc * 4;
-  off = (off + 15) / 16 * 16;
-  p.off_bar = off; off += 512;
-  const int smem_bytes = off + 1024;
-  SD_REQUIRE(smem_bytes <= SMEM_LIMIT, "conv_fwd_tc: shared-memory plan %d exceeds limit", smem_bytes);
+  SD_REQUIRE(p.a_rows <= 256, "conv_fwd_tc: dilation %d too large for one activation tile", a.dil);
+  if (g_conv_pair < 0) {
+    const char* e = getenv("SD_B200_CONV_PAIR");
+    g_conv_pair = (e && e[0] == '0') ? 0 : 1;
+    e = getenv("SD_B200_CONV_WS");
+    g_conv_ws = (e && e[0] == '1') ? 1 : 0;
+  }
+  // CTA pairs (M=256 MMAs, half the weight bytes per SM) whenever one weight tile serves both row tiles
+  // (measured at the cfg2 shapes, tools/bench_conv_pair.py: pairs win for the 3-tap convs, which are bound by the
+  //  weight stream, and lose for the short-K 1x1 convs, whose epilogues bound the tile time and get coupled)
+  const bool pair = g_conv_pair && a.widx == nullptr && a.B * p.m_tiles_per_sample >= 2 * sm_count() &&
+                    (g_conv_pair == 2 || a.taps == 3 || a.out_mode == SD_OUT_NCT_F32);
+  const int n_pairs = sm_count() / 2;
+  int w0 = 0, w1 = 0, smem_bytes = 0;
+
+  // shared-memory plan for column tile `bn`.  mode 0: one CTA per tile, weights streamed through a ring;
+  // 1: CTA pair, weights streamed; 2: CTA pair, weight-stationary (the pair keeps ALL taps x k-blocks of its
+  // column tile resident and walks down the row tiles, so only activations stream from L2).
+  auto plan = [&](int bn, int mode) -> bool {
+    p.block_n = bn;
+    if (glu) {
+      p.n_tiles = (p.Op + bn / 2 - 1) / (bn / 2);
+      p.cols_alloc = p.n_tiles * (bn / 2);
+    } else {
+      p.n_tiles = (a.Np + bn - 1) / bn;
+      p.cols_alloc = p.n_tiles * bn;
+    }
+    p.w_bytes = (mode >= 1 ? bn / 2 : bn) * BLOCK_K * 2;
+    const int nch = (glu ? bn / 2 : bn) / 16;
+    w0 = (nch + 1) / 2 * 16; w1 = nch / 2 * 16;            // column widths of the two warp halves
+    p.w0cols = w0;
+    const bool need_stg1 = glu || (a.act == SD_ACT_GELU && a.out_mode == SD_OUT_BTC);
+    const int stg_bytes = BLOCK_M * bn * 2;
+    const int stg1_bytes = need_stg1 ? BLOCK_M * (glu ? bn / 2 : bn) * 2 : 0;
+    const int stgr_bytes = a.res ? stg_bytes : 0;
+    const int stats_bytes = a.stats ? 8 * p.cols_alloc * 4 : 0;   // per TMEM quadrant: sums and sums of squares
+    const int tail = stg_bytes + stg1_bytes + stgr_bytes + (glu ? 2 : 1) * p.cols_alloc * 4 + stats_bytes + 16 + 512;
+    const int ring = SMEM_LIMIT - 1024 - tail;
+    int sa, sw, w_region;
+    if (mode == 2) {
+      if (p.k_blocks > 2 * MAX_W_SLOTS || p.n_tiles > n_pairs) return false;
+      w_region = a.taps * p.k_blocks * p.w_bytes;
+      sa = (ring - w_region) / p.a_bytes;
+      if (sa > MAX_A_SLOTS) sa = MAX_A_SLOTS;
+      if (sa < 2) return false;
+      sw = 0;
+    } else {
+      // taps==3: few activation slots (each feeds 3 weight tiles), the rest of the ring holds weight tiles
+      sa = a.taps == 3 ? 3 : (ring / (p.a_bytes + p.w_bytes));
+      if (a.taps == 3 && ring - sa * p.a_bytes < 5 * p.w_bytes) sa = 2;
+      if (sa > MAX_A_SLOTS) sa = MAX_A_SLOTS;
+      sw = (ring - sa * p.a_bytes) / p.w_bytes;
+      if (sw > MAX_W_SLOTS) sw = MAX_W_SLOTS;
+      if (a.taps == 3 && sw > 3 * sa + 3) sw = 3 * sa + 3;
+      if (sa < 1 || sw < 2) return false;
+      w_region = sw * p.w_bytes;
+    }
+    p.sa_slots = sa; p.sw_slots = sw;
+    p.off_w = sa * p.a_bytes;
+    int off = p.off_w + w_region;
+    p.off_stg0 = off; off += stg_bytes;
+    p.off_stg1 = off; off += stg1_bytes;
+    p.off_stgr = off; off += stgr_bytes;
+    p.off_bias = off; off += (glu ? 2 : 1) * p.cols_alloc * 4;
+    p.off_stats = off; off += stats_bytes;
+    off = (off + 15) / 16 * 16;
+    p.off_bar = off; off += 512;
+    smem_bytes = off + 1024;
+    return smem_bytes <= SMEM_LIMIT;
+  };
+  int mode = pair ? 1 : 0;
+  const int n_total = glu ? 2 * p.Op : a.Np, gran = glu ? 32 : 16;
+  if (pair && g_conv_ws) {   // widest column tile whose weights fit next to >= 2 activation slots
+    const int min_tiles = (n_total + MAX_BLOCK_N - 1) / MAX_BLOCK_N;
+    for (int nt = min_tiles; nt <= min_tiles + 8 && mode != 2; ++nt) {
+      const int bn = ((n_total + nt - 1) / nt + gran - 1) / gran * gran;
+      if (bn <= MAX_BLOCK_N && plan(bn, 2)) mode = 2;
+    }
+  }
+  if (mode != 2)
+    SD_REQUIRE(plan(pick_block_n(n_total, gran), mode), "conv_fwd_tc: operand rings do not fit (N=%d K=%d dil=%d)", a.N, a.Kp, a.dil);
+  p.num_mpairs = (a.B * p.m_tiles_per_sample + 1) / 2;
+  static const bool show_plan = getenv("SD_B200_SHOW_PLAN") != nullptr;
+  if (show_plan)
+    fprintf(stderr, "conv_fwd_tc plan: K=%d N=%d taps=%d dil=%d act=%d out=%d res=%d stats=%d | %s block_n=%d n_tiles=%d a_slots=%d w_slots=%d smem=%d\n",
+            a.Kp, a.N, a.taps, a.dil, a.act, a.out_mode, a.res != nullptr, a.stats != nullptr,
+            mode == 2 ? "pair weight-stationary" : mode == 1 ? "pair streaming" : "single-CTA streaming", p.block_n, p.n_tiles,
+            p.sa_slots, p.sw_slots, smem_bytes);
+  p.num_tiles = pair ? p.num_mpairs * p.n_tiles : a.B * p.m_tiles_per_sample * p.n_tiles;
 
   // tensor maps of the epilogue tensors: (cols, T, B) with a (w, 32, 1) box, no swizzle
   EpiMaps em;
@@ -688,13 +887,45 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
                    (uint64_t)a.Kp * 2, (uint64_t)a.Np * a.Kp * 2, BLOCK_K, (uint32_t)(p.block_n / 2), 1))
     return 1;
 
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const FwdParams);
+  static const KernelFn kernels[3][2] = {
+      {conv_fwd_tc_kernel<false, false, 1>, conv_fwd_tc_kernel<false, false, 3>},
+      {conv_fwd_tc_kernel<true, false, 1>, conv_fwd_tc_kernel<true, false, 3>},
+      {conv_fwd_tc_kernel<true, true, 1>, conv_fwd_tc_kernel<true, true, 3>}};
   static bool attr_set = false;
   if (!attr_set) {
-    SD_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    for (int m = 0; m < 3; ++m)
+      for (int t = 0; t < 2; ++t)
+        SD_CUDA(cudaFuncSetAttribute(kernels[m][t], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
-  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_fwd_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(ta, tw, em, p);
+  const KernelFn kernel = kernels[mode][a.taps == 3];
+  if (pair) {
+    int grid = 2 * (p.num_tiles < n_pairs ? p.num_tiles : n_pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    static int max_pairs = -1;
+    if (max_pairs < 0) {   // all pairs must be co-resident: the tile walk is statically strided
+      cudaLaunchConfig_t q = cfg;
+      q.dynamicSmemBytes = SMEM_LIMIT;
+      SD_CUDA(cudaOccupancyMaxActiveClusters(&max_pairs, kernels[1][1], &q));
+    }
+    if (2 * max_pairs < grid) { grid = 2 * max_pairs; cfg.gridDim = dim3(grid); }
+    SD_REQUIRE(grid >= 2 && (mode != 2 || grid / 2 >= p.n_tiles), "conv_fwd_tc: not enough resident CTA pairs (%d)", grid / 2);
+    SD_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tw, em, p));
+  } else {
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(ta, tw, em, p);
+  }
   return check_launch("conv_fwd_tc");
 }
 

@@ -29,8 +29,9 @@ def dtypes(precision=None):
 
 
 def set_impl(name: str):
-    """'auto' | 'simt' | 'tc' -- kernel family for conv / wgrad (tests)."""
-    nat.call("sd_set_impl", {"auto": nat.IMPL_AUTO, "simt": nat.IMPL_SIMT, "tc": nat.IMPL_TC}[name])
+    """'auto' | 'simt' | 'tc' | 'tc_1cta' | 'tc_ws' -- kernel family for conv / wgrad (tests)."""
+    nat.call("sd_set_impl", {"auto": nat.IMPL_AUTO, "simt": nat.IMPL_SIMT, "tc": nat.IMPL_TC, "tc_1cta": nat.IMPL_TC_1CTA,
+                                "tc_ws": nat.IMPL_TC_WS}[name])
 
 
 def rup8(c: int) -> int:

@@ -326,3 +326,76 @@ def test_clip_tensor_core_kernels(M, N, D, diag0):
     dz = ops.clip_dz_tc(coef_t, cz, x, z, gs)
     ref = 0.7 * (coef.double().T @ x.double() - cz.double()[:, None] * z.double())
     assert rel(dz, ref) < 3e-3
+
+
+@pytest.mark.parametrize("B,T,K,N,taps,dil,mode", [
+    (100, 360, 320, 320, 3, 4, "res_stats"),      # 300 row tiles: 150 CTA pairs' worth, two column tiles
+    (99, 360, 136, 640, 3, 2, "glu"),             # odd number of row tiles: the last pair has a dead half
+    (100, 360, 200, 1024, 1, 1, "gelu_nct"),      # final conv: NCT fp32 output + |Z|^2
+    (150, 200, 270, 270, 1, 1, "gelu_btc"),
+    (100, 300, 64, 48, 3, 16, "res_stats"),
+    (100, 360, 1100, 64, 1, 1, "gelu_btc"),       # 18 k-blocks: too many for resident weights, streaming pairs
+    (100, 360, 640, 320, 3, 2, "res_stats"),      # GLU-conv data gradient shape: narrow weight-stationary tiles
+])
+def test_conv_cta_pair_matches_single_cta(B, T, K, N, taps, dil, mode):
+    """The cta_group::2 (M=256) conv tiles must reproduce the single-CTA tcgen05 kernel bit for bit
+    (same accumulation order) and agree with the fp32 statement of the op."""
+    ops, nat = _ops()
+    dtype = torch.bfloat16
+    torch.manual_seed(3)
+    x = torch.randn(B, K, T, device=DEV)
+    w = torch.randn(N, K, taps, device=DEV) / (K * taps) ** 0.5
+    bias = torch.randn(N, device=DEV)
+    xt = ops.nct_to_btc(x, dtype)
+    wf, _ = pack(w, dtype)
+    Np = ops.rup8(N)
+    outs = {}
+    try:
+        for impl in ("tc_1cta", "tc", "tc_ws"):
+            ops.set_impl(impl)
+            r = {}
+            if mode == "res_stats":
+                torch.manual_seed(4)
+                rt = ops.nct_to_btc(torch.randn(B, N, T, device=DEV), dtype)
+                r["stats"] = torch.zeros((2, Np), dtype=torch.float64, device=DEV)
+                r["out"] = torch.empty((B, T, Np), dtype=dtype, device=DEV)
+                ops.conv_fwd(xt, wf, K=K, N=N, taps=taps, dil=dil, bias=bias, res=rt, out=r["out"], stats=r["stats"])
+                r["res"] = rt
+            elif mode == "glu":
+                r["pre"] = torch.empty((B, T, Np), dtype=dtype, device=DEV)
+                r["out"] = torch.empty((B, T, ops.rup8(N // 2)), dtype=dtype, device=DEV)
+                ops.conv_fwd(xt, wf, K=K, N=N, taps=taps, dil=dil, bias=bias, out=r["out"], preact=r["pre"], act=nat.ACT_GLU)
+            elif mode == "gelu_nct":
+                r["pre"] = torch.empty((B, T, Np), dtype=dtype, device=DEV)
+                r["out"] = torch.empty((B, N, T), dtype=torch.float32, device=DEV)
+                r["n2"] = torch.zeros((B,), dtype=torch.float32, device=DEV)
+                ops.conv_fwd(xt, wf, K=K, N=N, bias=bias, out=r["out"], preact=r["pre"], act=nat.ACT_GELU,
+                             out_mode=nat.OUT_NCT_F32, rownorm2=r["n2"])
+            else:
+                r["pre"] = torch.empty((B, T, Np), dtype=dtype, device=DEV)
+                r["out"] = torch.empty((B, T, Np), dtype=dtype, device=DEV)
+                ops.conv_fwd(xt, wf, K=K, N=N, bias=bias, out=r["out"], preact=r["pre"], act=nat.ACT_GELU)
+            torch.cuda.synchronize()
+            outs[impl] = r
+    finally:
+        ops.set_impl("auto")
+    a = outs["tc_1cta"]
+    for other in ("tc", "tc_ws"):     # streaming pairs, weight-stationary pairs
+        b = outs[other]
+        assert torch.equal(a["out"], b["out"]), other
+        if "pre" in a:
+            assert torch.equal(a["pre"], b["pre"]), other
+        if "stats" in a:
+            assert rel(b["stats"], a["stats"]) < 1e-6
+        if "n2" in a:
+            assert rel(b["n2"], a["n2"]) < 1e-5
+            assert rel(b["n2"], (b["out"] ** 2).sum(dim=(1, 2))) < 1e-4
+    y = F.conv1d(x, w, bias, padding=dil * (taps // 2), dilation=dil)
+    if mode == "res_stats":
+        assert rel(ops.btc_to_nct(b["out"], N), y + ops.btc_to_nct(a["res"], N)) < TOL[dtype]
+    elif mode == "glu":
+        assert rel(ops.btc_to_nct(b["out"], N // 2), F.glu(y, dim=-2)) < TOL[dtype]
+    elif mode == "gelu_nct":
+        assert rel(b["out"], F.gelu(y, approximate="tanh")) < TOL[dtype]
+    else:
+        assert rel(ops.btc_to_nct(b["out"], N), F.gelu(y, approximate="tanh")) < TOL[dtype]
