@@ -50,22 +50,32 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / power / throttle reasons, sampled every ~10 ms by a background process that is started
+    before the warm-up; only the samples whose timestamp falls inside the timed region are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", "10"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -74,19 +84,23 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm = []
+        sm, pw = [], []
         reasons = set()
         for r in rows:
             try:
-                sm.append(float(r[0])); out["sm_max_mhz"] = float(r[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.t0 is not None and not (self.t0 <= ts <= self.t1):
+                    continue
+                sm.append(float(r[1])); out["sm_max_mhz"] = float(r[2]); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.strip().lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
         if sm:
-            busy = sorted(sm)[len(sm) // 2:]           # upper half = samples under load
-            out["sm_mhz"] = float(np.median(busy))
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_min_mhz"] = float(min(sm))
+            out["power_w"] = float(np.median(pw))
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out
@@ -197,18 +211,22 @@ def run_ours(a, rank, world, local_rank):
         counter["n"] += 1
         return orig_call(name, *args_)
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(a.warmup):
         hot_step()
     barrier()
     nat.call = counting_call
     ops.nat.call = counting_call
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if clocks:
+        clocks.mark_start()
     e0.record()
     for _ in range(a.steps):
         loss = hot_step()
     e1.record()
     barrier()
+    if clocks:
+        clocks.mark_end()
     launches = counter["n"]
     nat.call = orig_call
     ops.nat.call = orig_call
