@@ -200,6 +200,20 @@ int sd_clip_dots_tc(const float* x, const float* z, float* dots, void* workspace
 int sd_clip_dz_tc(const float* coef_t, const float* cz, const float* x, const float* z, float* dz,
                   const float* gscale, int M, int N, int64_t D, void* stream);
 
+/* bf16 transport of the speech rows for data-parallel training (sd_b200/dist.py; the reference is single-device,
+ * loss.py:60-71 sees the whole batch): every rank rounds its rows to bf16 once, the all-gather moves and the two
+ * GEMMs re-read half the bytes, and the GEMMs run as tcgen05 kind::f16.  Need D % 8 == 0.
+ *   sd_cast_rows_bf16:   y (M,D) bf16 = round(x); nrm2[i] = |y_i|^2 (norms of the ROUNDED rows)
+ *   sd_clip_coef_t_bf16: coef_t (N, Mp) bf16 = coef^T, Mp = roundup8(M), pad columns zero
+ *   sd_clip_dots_tc_bf16 / sd_clip_dz_tc_bf16: as the tf32 forms with x, z (dots) and coef_t, x (dz) in bf16;
+ *   the projection row z and dz stay fp32. */
+int sd_cast_rows_bf16(const float* x, void* y, float* nrm2, int M, int64_t D, void* stream);
+int sd_clip_coef_t_bf16(const float* coef, void* coef_t, int M, int N, int Mp, void* stream);
+int sd_clip_dots_tc_bf16(const void* x, const void* z, float* dots, void* workspace, int M, int N, int64_t D,
+                         void* stream);
+int sd_clip_dz_tc_bf16(const void* coef_t, const float* cz, const void* x, const float* z, float* dz,
+                       const float* gscale, int M, int N, int64_t D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,53 @@ int rownorm2_launch(const float* x, float* out, int M, int64_t D, int accumulate
   return check_launch("rownorm2");
 }
 
+// ---- fp32 rows -> bf16 rows + squared norms of the ROUNDED rows (data-parallel CLIP transport) ------
+// One pass: the gathered speech rows travel over NVLink and are re-read by the similarity / gradient GEMMs
+// in bf16; the norms are those of the values the GEMMs see, so the cosine stays self-consistent.
+__global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                             float* __restrict__ out, int64_t D, int64_t chunk) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  const int64_t d0 = (int64_t)blockIdx.y * chunk, d1 = min(D, d0 + chunk);
+  const float* row = x + (size_t)i * D;
+  __nv_bfloat16* orow = y + (size_t)i * D;
+  float s = 0.f;
+  for (int64_t d = d0 + threadIdx.x * 8; d < d1; d += 2048) {     // D % 8 == 0 on this path
+    const float4 a = *reinterpret_cast<const float4*>(row + d), b = *reinterpret_cast<const float4*>(row + d + 4);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(orow + d) = o;
+    const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1), f2 = __bfloat1622float2(p2), f3 = __bfloat1622float2(p3);
+    s += f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out + i, t);
+  }
+}
+
+// coefT[j, i] (bf16, row stride Mp) = coef[i, j]: A operand of the bf16 gradient GEMM
+__global__ void coef_t_bf16_kernel(const float* __restrict__ coef, __nv_bfloat16* __restrict__ ct, int M, int N, int Mp) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < M && j < N) ? coef[(size_t)i * N + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + threadIdx.x;
+    if (j < N && i < Mp) ct[(size_t)j * Mp + i] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+  }
+}
+
 // ---- dots[i,j] += sum_d x[i,d] z[j,d]  (split-K, 64x64 tiles) -------------------------------------
 constexpr int CB = 64, CK = 16;
 
@@ -249,11 +296,11 @@ clip_dz_kernel(const float* __restrict__ coef, const float* __restrict__ cz, con
 }  // namespace sd
 
 namespace sd {
-bool clip_tc_supported(int M, int N, int64_t D, const void* x, const void* z);
+bool clip_tc_supported(int M, int N, int64_t D, const void* x, const void* z, bool bf16);
 size_t clip_dots_tc_workspace(int M, int N, int64_t D);
-int clip_dots_tc(const float* x, const float* z, float* dots, float* workspace, int M, int N, int64_t D, cudaStream_t st);
-int clip_dz_tc(const float* coef_t, const float* cz, const float* x, const float* z, float* dz, const float* gscale,
-               int M, int N, int64_t D, cudaStream_t st);
+int clip_dots_tc(const void* x, const void* z, float* dots, float* workspace, int M, int N, int64_t D, bool bf16, cudaStream_t st);
+int clip_dz_tc(const void* coef_t, const float* cz, const void* x, const float* z, float* dz, const float* gscale,
+               int M, int N, int64_t D, bool bf16, cudaStream_t st);
 }  // namespace sd
 
 using namespace sd;
@@ -266,16 +313,48 @@ int64_t sd_clip_dots_workspace_bytes(int M, int N, int64_t D) {
 }
 
 int sd_clip_dots_tc(const float* x, const float* z, float* dots, void* workspace, int M, int N, int64_t D, void* stream) {
-  SD_REQUIRE(clip_tc_supported(M, N, D, x, z), "sd_clip_dots_tc: unsupported shape/alignment (D %% 4 != 0?)");
+  SD_REQUIRE(clip_tc_supported(M, N, D, x, z, false), "sd_clip_dots_tc: unsupported shape/alignment (D %% 4 != 0?)");
   SD_REQUIRE(workspace != nullptr, "sd_clip_dots_tc: workspace is null");
-  return clip_dots_tc(x, z, dots, reinterpret_cast<float*>(workspace), M, N, D, (cudaStream_t)stream);
+  return clip_dots_tc(x, z, dots, reinterpret_cast<float*>(workspace), M, N, D, false, (cudaStream_t)stream);
+}
+
+int sd_clip_dots_tc_bf16(const void* x, const void* z, float* dots, void* workspace, int M, int N, int64_t D, void* stream) {
+  SD_REQUIRE(clip_tc_supported(M, N, D, x, z, true), "sd_clip_dots_tc_bf16: unsupported shape/alignment (D %% 8 != 0?)");
+  SD_REQUIRE(workspace != nullptr, "sd_clip_dots_tc_bf16: workspace is null");
+  return clip_dots_tc(x, z, dots, reinterpret_cast<float*>(workspace), M, N, D, true, (cudaStream_t)stream);
+}
+
+int sd_clip_dz_tc_bf16(const void* coef_t, const float* cz, const void* x, const float* z, float* dz, const float* gscale,
+                       int M, int N, int64_t D, void* stream) {
+  SD_REQUIRE(clip_tc_supported(M, N, D, x, z, true), "sd_clip_dz_tc_bf16: unsupported shape/alignment (D %% 8 != 0?)");
+  SD_REQUIRE(coef_t != nullptr && (((uintptr_t)coef_t) & 15) == 0 && (((uintptr_t)dz) & 15) == 0, "sd_clip_dz_tc_bf16: bad pointers");
+  return clip_dz_tc(coef_t, cz, x, z, dz, gscale, M, N, D, true, (cudaStream_t)stream);
+}
+
+int sd_cast_rows_bf16(const float* x, void* y, float* nrm2, int M, int64_t D, void* stream) {
+  SD_REQUIRE(D % 8 == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)y) & 15) == 0, "sd_cast_rows_bf16: D %% 8 != 0 or unaligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  SD_CUDA(cudaMemsetAsync(nrm2, 0, sizeof(float) * M, st));
+  int splits = cdiv(148 * 8, M);
+  int64_t chunk = (D + splits - 1) / splits;
+  chunk = (chunk + 2047) / 2048 * 2048;
+  splits = cdiv(D, chunk);
+  cast_rows_bf16_kernel<<<dim3(M, splits), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), nrm2, D, chunk);
+  return check_launch("cast_rows_bf16");
+}
+
+int sd_clip_coef_t_bf16(const float* coef, void* coef_t, int M, int N, int Mp, void* stream) {
+  SD_REQUIRE(Mp >= M && Mp % 8 == 0, "sd_clip_coef_t_bf16: Mp must be M rounded up to a multiple of 8");
+  coef_t_bf16_kernel<<<dim3(cdiv(Mp, 32), cdiv(N, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      coef, reinterpret_cast<__nv_bfloat16*>(coef_t), M, N, Mp);
+  return check_launch("clip_coef_t_bf16");
 }
 
 int sd_clip_dz_tc(const float* coef_t, const float* cz, const float* x, const float* z, float* dz, const float* gscale,
                   int M, int N, int64_t D, void* stream) {
-  SD_REQUIRE(clip_tc_supported(M, N, D, x, z), "sd_clip_dz_tc: unsupported shape/alignment (D %% 4 != 0?)");
+  SD_REQUIRE(clip_tc_supported(M, N, D, x, z, false), "sd_clip_dz_tc: unsupported shape/alignment (D %% 4 != 0?)");
   SD_REQUIRE(coef_t != nullptr && (((uintptr_t)dz) & 15) == 0, "sd_clip_dz_tc: bad pointers");
-  return clip_dz_tc(coef_t, cz, x, z, dz, gscale, M, N, D, (cudaStream_t)stream);
+  return clip_dz_tc(coef_t, cz, x, z, dz, gscale, M, N, D, false, (cudaStream_t)stream);
 }
 
 int sd_rownorm2(const float* x, float* nrm2, int M, int64_t D, void* stream) {

@@ -26,7 +26,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // ======================================================================================================
 // (1) similarity, split-K
 // ======================================================================================================
-constexpr int DK = 32;                       // 32 fp32 = 128 B per K block row
+constexpr int DK = 32;                       // 32 fp32 = 128 B per K block row (64 bf16 in the bf16 variant)
 constexpr int D_STAGES = 3;
 constexpr int D_A_BYTES = 2 * 128 * 128;     // two 128-row halves
 constexpr int D_B_BYTES = 256 * 128;
@@ -38,9 +38,13 @@ struct DotsParams {
   long long kblocks_total, kblocks_per_split;
 };
 
+// BF16: both operands are bf16 rows (kind::f16, 64 elements per 128-byte K block) -- the data-parallel path,
+// where the gathered speech rows travel and are stored in bf16; otherwise tf32 on fp32 rows.
+template <bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 clip_dots_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
                     const DotsParams p) {
+  constexpr int KB_ELEMS = BF16 ? 2 * DK : DK;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + D_STAGES * D_STAGE_BYTES;
@@ -80,7 +84,7 @@ clip_dots_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_wait(empty_bar(s), ph ^ 1);
       if (elect_one_sync()) {
         const uint32_t sa = smem_base + s * D_STAGE_BYTES, sb = sa + D_A_BYTES;
-        const int kc = (int)((kb0 + it) * DK);
+        const int kc = (int)((kb0 + it) * KB_ELEMS);
         mbar_arrive_expect_tx(full_bar(s), tx);
         tma_load_3d(sa, &tmap_x, full_bar(s), kc, m_pair * 256, 0);
         tma_load_3d(sa + 128 * 128, &tmap_x, full_bar(s), kc, m_pair * 256 + 128, 0);
@@ -90,7 +94,7 @@ clip_dots_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       if (++s == D_STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(/*tf32*/ 2, 0, 0, 128, (uint32_t)p.block_n);
+    const uint32_t idesc = make_idesc(BF16 ? /*bf16*/ 1 : /*tf32*/ 2, 0, 0, 128, (uint32_t)p.block_n);
     const uint32_t dhi = smem_desc_hi(1024);
     int s = 0; uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
@@ -100,9 +104,14 @@ clip_dots_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const uint32_t alo = smem_desc_lo(smem_base + s * D_STAGE_BYTES, 16);
         const uint32_t a2lo = alo + ((128 * 128) >> 4), blo = alo + (D_A_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < DK / 8; ++k) {
-          umma_tf32(tmem_base, desc64(alo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
-          umma_tf32(tmem_base + 256, desc64(a2lo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
+        for (int k = 0; k < DK / 8; ++k) {   // 32 bytes of K per MMA for both element types
+          if (BF16) {
+            umma_f16(tmem_base, desc64(alo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
+            umma_f16(tmem_base + 256, desc64(a2lo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
+          } else {
+            umma_tf32(tmem_base, desc64(alo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
+            umma_tf32(tmem_base + 256, desc64(a2lo + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (it | k) != 0);
+          }
         }
         umma_commit(empty_bar(s));
         if (it == iters - 1) umma_commit(tfull_bar);
@@ -175,9 +184,13 @@ struct DzParams {
   int j_tiles, num_tiles, k_blocks;
 };
 
+// BF16: coefT and x are bf16 (kind::f16): 64 global rows i per k-block; x as the MN-major operand uses the plain
+// 128-byte swizzle (64 contiguous d per K row, 8-row atoms, one 8 KB block per 64 columns of d).  z and dz stay fp32.
+template <bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 clip_dz_tc_kernel(const __grid_constant__ CUtensorMap tmap_ct, const __grid_constant__ CUtensorMap tmap_x,
                   const DzParams p) {
+  constexpr int KB_ROWS = BF16 ? 2 * Z_BK : Z_BK;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + Z_STAGES * Z_STAGE_BYTES;
@@ -215,18 +228,25 @@ clip_dz_tc_kernel(const __grid_constant__ CUtensorMap tmap_ct, const __grid_cons
         if (elect_one_sync()) {
           const uint32_t sa = smem_base + s * Z_STAGE_BYTES, sb = sa + Z_A_BYTES;
           mbar_arrive_expect_tx(full_bar(s), Z_STAGE_BYTES);
-          tma_load_3d(sa, &tmap_ct, full_bar(s), kb * Z_BK, j_tile * Z_BM, 0);
+          tma_load_3d(sa, &tmap_ct, full_bar(s), kb * KB_ROWS, j_tile * Z_BM, 0);
+          if (BF16) {
 #pragma unroll
-          for (int a = 0; a < Z_BN / 32; ++a)
-            tma_load_3d(sb + a * Z_ATOM, &tmap_x, full_bar(s), (int)(d0 + 32 * a), kb * Z_BK, 0);
+            for (int a = 0; a < Z_BN / 64; ++a)
+              tma_load_3d(sb + a * (Z_B_BYTES / 2), &tmap_x, full_bar(s), (int)(d0 + 64 * a), kb * KB_ROWS, 0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < Z_BN / 32; ++a)
+              tma_load_3d(sb + a * Z_ATOM, &tmap_x, full_bar(s), (int)(d0 + 32 * a), kb * Z_BK, 0);
+          }
         }
         __syncwarp();
         if (++s == Z_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(/*tf32*/ 2, /*A K-major*/ 0, /*B MN-major*/ 1, Z_BM, Z_BN);
-    const uint32_t ahi = smem_desc_hi(1024), bhi = smem_desc_hi(512, /*SWIZZLE_128B_BASE32B*/ 1);
+    const uint32_t idesc = make_idesc(BF16 ? /*bf16*/ 1 : /*tf32*/ 2, /*A K-major*/ 0, /*B MN-major*/ 1, Z_BM, Z_BN);
+    const uint32_t ahi = smem_desc_hi(1024);
+    const uint32_t bhi = BF16 ? smem_desc_hi(1024) : smem_desc_hi(512, /*SWIZZLE_128B_BASE32B*/ 1);
     int s = 0; uint32_t ph = 0; int it_tile = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it_tile) {
       const int acc = it_tile & 1;
@@ -239,11 +259,14 @@ clip_dz_tc_kernel(const __grid_constant__ CUtensorMap tmap_ct, const __grid_cons
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t alo = smem_desc_lo(smem_base + s * Z_STAGE_BYTES, 16);
-          const uint32_t blo = smem_desc_lo(smem_base + s * Z_STAGE_BYTES + Z_A_BYTES, Z_ATOM);
+          const uint32_t blo = smem_desc_lo(smem_base + s * Z_STAGE_BYTES + Z_A_BYTES, BF16 ? Z_B_BYTES / 2 : Z_ATOM);
 #pragma unroll
-          for (int k = 0; k < Z_BK / 8; ++k)
-            // A: 8 fp32 (32 B) further along the swizzled row; B: next 8 K-rows (two 4-row swizzle groups, 1024 B)
-            umma_tf32(d_tmem, desc64(alo + 2 * k, ahi), desc64(blo + k * (1024 >> 4), bhi), idesc, (kb | k) != 0);
+          for (int k = 0; k < Z_BK / 8; ++k) {
+            // A: 32 B further along the swizzled row.  B tf32: next 8 K-rows (two 4-row swizzle groups, 1024 B);
+            // B bf16: next 16 K-rows (two 8-row atoms, 2048 B)
+            if (BF16) umma_f16(d_tmem, desc64(alo + 2 * k, ahi), desc64(blo + k * (2048 >> 4), bhi), idesc, (kb | k) != 0);
+            else umma_tf32(d_tmem, desc64(alo + 2 * k, ahi), desc64(blo + k * (1024 >> 4), bhi), idesc, (kb | k) != 0);
+          }
           umma_commit(empty_bar(s));
           if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
         }
@@ -326,8 +349,8 @@ int sms() {
 
 }  // namespace
 
-bool clip_tc_supported(int M, int N, int64_t D, const void* x, const void* z) {
-  if (D % 4 != 0 || D < 64) return false;                 // TMA needs 16-byte row strides
+bool clip_tc_supported(int M, int N, int64_t D, const void* x, const void* z, bool bf16) {
+  if (D % (bf16 ? 8 : 4) != 0 || D < 64) return false;    // TMA needs 16-byte row strides
   if (((uintptr_t)x & 15) || ((uintptr_t)z & 15)) return false;
   if (M < 1 || N < 1) return false;
   return true;
@@ -341,7 +364,7 @@ size_t clip_dots_tc_workspace(int M, int N, int64_t D) {
   return (size_t)nsplit * M * N * sizeof(float);
 }
 
-int clip_dots_tc(const float* x, const float* z, float* dots, float* workspace, int M, int N, int64_t D, cudaStream_t st) {
+int clip_dots_tc(const void* x, const void* z, float* dots, float* workspace, int M, int N, int64_t D, bool bf16, cudaStream_t st) {
   DotsParams p;
   memset(&p, 0, sizeof(p));
   p.part = workspace; p.M = M; p.N = N;
@@ -350,44 +373,58 @@ int clip_dots_tc(const float* x, const float* z, float* dots, float* workspace, 
   p.n_tiles = (N + p.block_n - 1) / p.block_n;
   p.nsplit = sms() / (p.m_pairs * p.n_tiles);
   if (p.nsplit < 1) p.nsplit = 1;
-  p.kblocks_total = (D + DK - 1) / DK;
+  const int kb_elems = bf16 ? 2 * DK : DK, esz = bf16 ? 2 : 4;
+  const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  p.kblocks_total = (D + kb_elems - 1) / kb_elems;
   p.kblocks_per_split = (p.kblocks_total + p.nsplit - 1) / p.nsplit;
   CUtensorMap tx, tz;
-  if (make_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, (uint64_t)D, (uint64_t)M, 1, (uint64_t)D * 4, (uint64_t)D * 4 * M, DK, 128, 1)) return 1;
-  if (make_tmap_3d(&tz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, z, (uint64_t)D, (uint64_t)N, 1, (uint64_t)D * 4, (uint64_t)D * 4 * N, DK, (uint32_t)p.block_n, 1)) return 1;
+  if (make_tmap_3d(&tx, dt, x, (uint64_t)D, (uint64_t)M, 1, (uint64_t)D * esz, (uint64_t)D * esz * M, kb_elems, 128, 1)) return 1;
+  if (make_tmap_3d(&tz, dt, z, (uint64_t)D, (uint64_t)N, 1, (uint64_t)D * esz, (uint64_t)D * esz * N, kb_elems, (uint32_t)p.block_n, 1)) return 1;
   static bool attr = false;
   if (!attr) {
-    SD_CUDA(cudaFuncSetAttribute(clip_dots_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    SD_CUDA(cudaFuncSetAttribute(clip_dots_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    SD_CUDA(cudaFuncSetAttribute(clip_dots_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr = true;
   }
   const int smem = D_STAGES * D_STAGE_BYTES + 256 + 1024;
-  clip_dots_tc_kernel<<<p.m_pairs * p.n_tiles * p.nsplit, NUM_THREADS, smem, st>>>(tx, tz, p);
+  if (bf16) clip_dots_tc_kernel<true><<<p.m_pairs * p.n_tiles * p.nsplit, NUM_THREADS, smem, st>>>(tx, tz, p);
+  else clip_dots_tc_kernel<false><<<p.m_pairs * p.n_tiles * p.nsplit, NUM_THREADS, smem, st>>>(tx, tz, p);
   if (check_launch("clip_dots_tc")) return 1;
   const int64_t mn = (int64_t)M * N;
   sum_partials_kernel<<<cdiv(mn, 256), 256, 0, st>>>(workspace, dots, mn, p.nsplit);
   return check_launch("clip_sum_partials");
 }
 
-int clip_dz_tc(const float* coef_t, const float* cz, const float* x, const float* z, float* dz, const float* gscale,
-               int M, int N, int64_t D, cudaStream_t st) {
+int clip_dz_tc(const void* coef_t, const float* cz, const void* x, const float* z, float* dz, const float* gscale,
+               int M, int N, int64_t D, bool bf16, cudaStream_t st) {
   DzParams p;
   memset(&p, 0, sizeof(p));
   p.z = z; p.cz = cz; p.gscale = gscale; p.dz = dz; p.M = M; p.N = N; p.D = D;
   p.j_tiles = (N + Z_BM - 1) / Z_BM;
   p.num_tiles = p.j_tiles * (int)((D + Z_BN - 1) / Z_BN);
-  p.k_blocks = (M + Z_BK - 1) / Z_BK;
-  const int Mp = (M + 3) / 4 * 4;   // coefT rows are padded to a 16-byte stride by the caller
+  const int kb_rows = bf16 ? 2 * Z_BK : Z_BK;
+  p.k_blocks = (M + kb_rows - 1) / kb_rows;
   CUtensorMap tc_, tx;
-  if (make_tmap_3d(&tc_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, coef_t, (uint64_t)M, (uint64_t)N, 1, (uint64_t)Mp * 4, (uint64_t)Mp * 4 * N, Z_BK, Z_BM, 1)) return 1;
-  if (make_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, (uint64_t)D, (uint64_t)M, 1, (uint64_t)D * 4, (uint64_t)D * 4 * M, 32, Z_BK, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+  if (bf16) {
+    const int Mp = (M + 7) / 8 * 8;   // coefT rows are padded to a 16-byte stride by the caller
+    const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if (make_tmap_3d(&tc_, BF, coef_t, (uint64_t)M, (uint64_t)N, 1, (uint64_t)Mp * 2, (uint64_t)Mp * 2 * N, kb_rows, Z_BM, 1)) return 1;
+    if (make_tmap_3d(&tx, BF, x, (uint64_t)D, (uint64_t)M, 1, (uint64_t)D * 2, (uint64_t)D * 2 * M, 64, kb_rows, 1)) return 1;
+  } else {
+    const int Mp = (M + 3) / 4 * 4;
+    if (make_tmap_3d(&tc_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, coef_t, (uint64_t)M, (uint64_t)N, 1, (uint64_t)Mp * 4, (uint64_t)Mp * 4 * N, Z_BK, Z_BM, 1)) return 1;
+    if (make_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, (uint64_t)D, (uint64_t)M, 1, (uint64_t)D * 4, (uint64_t)D * 4 * M, 32, Z_BK, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+  }
   static bool attr = false;
   if (!attr) {
-    SD_CUDA(cudaFuncSetAttribute(clip_dz_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    SD_CUDA(cudaFuncSetAttribute(clip_dz_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    SD_CUDA(cudaFuncSetAttribute(clip_dz_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr = true;
   }
   const int smem = Z_STAGES * Z_STAGE_BYTES + Z_BM * Z_PITCH + 256 + 1024;
   const int grid = p.num_tiles < sms() ? p.num_tiles : sms();
-  clip_dz_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(tc_, tx, p);
+  if (bf16) clip_dz_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tc_, tx, p);
+  else clip_dz_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tc_, tx, p);
   return check_launch("clip_dz_tc");
 }
 

@@ -39,6 +39,31 @@ def all_gather_rows(x, group):
     return out
 
 
+def gather_speech_rows(x2d, group, allow_bf16=True, async_op=False):
+    """All-gather the speech rows of every rank.  In the bf16 mode (and when no gradient flows to them) the rows are
+    rounded to bf16 ONCE on the owning rank together with their squared norms: the gather then moves, and the two
+    CLIP GEMMs re-read, half the bytes.  Returns (rows, norms-or-None[, works])."""
+    from . import ops
+    world, _ = world_rank(group)
+    works = []
+    if world > 1 and allow_bf16 and x2d.is_cuda and ops.clip_bf16_ok(x2d):
+        with torch.cuda.device(x2d.device), ops.stream_scope():
+            xb, n2 = ops.cast_rows_bf16(x2d)
+        rows = torch.empty((world * xb.shape[0], xb.shape[1]), dtype=xb.dtype, device=xb.device)
+        norms = torch.empty((world * n2.shape[0],), dtype=n2.dtype, device=n2.device)
+        works.append(dist.all_gather_into_tensor(norms, n2, group=group, async_op=async_op))
+        works.append(dist.all_gather_into_tensor(rows, xb, group=group, async_op=async_op))
+        keep = (xb, n2)
+    else:
+        rows = torch.empty((world * x2d.shape[0], x2d.shape[1]), dtype=x2d.dtype, device=x2d.device)
+        norms = None
+        works.append(dist.all_gather_into_tensor(rows, x2d.contiguous(), group=group, async_op=async_op))
+        keep = (x2d,)
+    if async_op:
+        return rows, norms, works, keep
+    return rows, norms
+
+
 def all_reduce_sum(t, group):
     t = t.contiguous()
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -126,8 +151,7 @@ class DataParallel:
         y2 = Y.reshape(Y.shape[0], -1)
         if y2.dtype != torch.float32 or not y2.is_contiguous():
             y2 = y2.float().contiguous()
-        out = torch.empty((world * y2.shape[0], y2.shape[1]), dtype=y2.dtype, device=y2.device)
-        work = dist.all_gather_into_tensor(out, y2, group=self.group, async_op=True)
-        self.loss_fn._prefetched = (Y.data_ptr(), tuple(Y.shape), work, out, y2)
+        rows, norms, works, keep = gather_speech_rows(y2, self.group, not Y.requires_grad, async_op=True)
+        self.loss_fn._prefetched = (Y.data_ptr(), tuple(Y.shape), works, rows, norms, keep)
         # the temperature gradient is a partial sum per rank: the loss Function already
         # all-reduces `partial`, so dtemp is global -- nothing more to do for it.

@@ -205,9 +205,29 @@ def clip_tc_ok(x2d, z2d):
             and nat.lib().sd_clip_dots_workspace_bytes(M, z2d.shape[0], D) > 0)
 
 
+def cast_rows_bf16(x2d):
+    """fp32 rows -> (bf16 rows, squared norms of the rounded rows); one pass."""
+    M, D = x2d.shape
+    y = torch.empty((M, D), dtype=torch.bfloat16, device=x2d.device)
+    n2 = torch.empty((M,), dtype=torch.float32, device=x2d.device)
+    nat.call("sd_cast_rows_bf16", _p(x2d), _p(y), _p(n2), M, D, _st())
+    return y, n2
+
+
+def clip_bf16_ok(x2d):
+    """bf16 transport of the speech rows (data-parallel CLIP): bf16 mode and rows TMA can address"""
+    return get_precision() == "bf16" and x2d.shape[1] % 8 == 0 and x2d.shape[1] >= 64
+
+
 def clip_dots(x2d, z2d, tc=False):
     M, D = x2d.shape
     Nn = z2d.shape[0]
+    if x2d.dtype == torch.bfloat16:
+        ws_bytes = nat.lib().sd_clip_dots_workspace_bytes(M, Nn, D)
+        ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x2d.device)
+        dots = torch.empty((M, Nn), dtype=torch.float32, device=x2d.device)
+        nat.call("sd_clip_dots_tc_bf16", _p(x2d), _p(z2d), _p(dots), _p(ws), M, Nn, D, _st())
+        return dots
     if tc:
         ws_bytes = nat.lib().sd_clip_dots_workspace_bytes(M, Nn, D)
         ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=x2d.device)
@@ -247,6 +267,18 @@ def clip_dz_tc(coef_t, cz, x2d, z2d, gscale=None):
     Nn = z2d.shape[0]
     dz = torch.empty((Nn, D), dtype=torch.float32, device=x2d.device)
     nat.call("sd_clip_dz_tc", _p(coef_t), _p(cz), _p(x2d), _p(z2d), _p(dz), _p(gscale), M, Nn, D, _st())
+    return dz
+
+
+def clip_dz_bf16(coef, cz, xb, z2d, gscale=None):
+    """dz with coef (M,Nn) fp32 -> transposed bf16 A operand, xb (M,D) bf16 rows, z2d (Nn,D) fp32."""
+    M, D = xb.shape
+    Nn = z2d.shape[0]
+    Mp = (M + 7) // 8 * 8
+    ct = torch.empty((Nn, Mp), dtype=torch.bfloat16, device=xb.device)
+    nat.call("sd_clip_coef_t_bf16", _p(coef), _p(ct), M, Nn, Mp, _st())
+    dz = torch.empty((Nn, D), dtype=torch.float32, device=xb.device)
+    nat.call("sd_clip_dz_tc_bf16", _p(ct), _p(cz), _p(xb), _p(z2d), _p(dz), _p(gscale), M, Nn, D, _st())
     return dz
 
 

@@ -39,22 +39,34 @@ class _ClipFn(torch.autograd.Function):
     data-parallel), z = local brain rows."""
 
     @staticmethod
-    def forward(ctx, x, z, temp, reduction, use_temp, group, zn2_hint):
+    def forward(ctx, x, z, temp, reduction, use_temp, group, zn2_hint, xn2_hint):
+        """x: fp32 rows, or (data-parallel bf16 transport) bf16 rows with their squared norms in xn2_hint."""
         M, Nn = x.shape[0], z.shape[0]
         world, rank = sd_dist.world_rank(group)
         with torch.cuda.device(x.device), ops.stream_scope():
-            tc = ops.clip_tc_ok(x, z)          # bf16 mode: TF32 tensor-core GEMMs; fp32 mode: exact fp32
-            xn2 = ops.rownorm2(x)
-            zn2 = zn2_hint if zn2_hint is not None else ops.rownorm2(z)
-            dots = ops.clip_dots(x, z, tc=tc)
+            if x.dtype == torch.bfloat16:
+                tc = True
+                xn2 = xn2_hint
+                zb, zn2 = ops.cast_rows_bf16(z)      # the brain rows as the bf16 GEMM sees them
+                dots = ops.clip_dots(x, zb)
+                del zb
+            else:
+                tc = ops.clip_tc_ok(x, z)          # bf16 mode: TF32 tensor-core GEMMs; fp32 mode: exact fp32
+                xn2 = ops.rownorm2(x)
+                zn2 = zn2_hint if zn2_hint is not None else ops.rownorm2(z)
+                dots = ops.clip_dots(x, z, tc=tc)
             t = temp.detach() if use_temp else torch.zeros_like(temp)
             logits, row_stat, col_lse = ops.clip_phase1(dots, xn2, zn2, t)
             if world > 1:
                 row_stat = sd_dist.merge_row_stats(row_stat, group)
             row_lse = row_stat[:, 0] + torch.log(row_stat[:, 1])
             scale = 1.0 / M if reduction == "mean" else 1.0
-            coef, coef_t, cz, partial = ops.clip_phase2(logits, row_lse, col_lse, xn2, zn2, t, scale, rank * Nn,
-                                                        want_t=True)
+            if x.dtype == torch.bfloat16:      # the bf16 gradient GEMM makes its own transposed bf16 operand
+                coef, cz, partial = ops.clip_phase2(logits, row_lse, col_lse, xn2, zn2, t, scale, rank * Nn)
+                coef_t = coef                  # placeholder in the saved tuple
+            else:
+                coef, coef_t, cz, partial = ops.clip_phase2(logits, row_lse, col_lse, xn2, zn2, t, scale, rank * Nn,
+                                                            want_t=True)
             if world > 1:
                 partial = sd_dist.all_reduce_sum(partial, group)
         ctx.save_for_backward(x, z, coef, cz, partial, logits, xn2, zn2, t, coef_t)
@@ -70,15 +82,19 @@ class _ClipFn(torch.autograd.Function):
         with torch.cuda.device(x.device), ops.stream_scope():
             if ctx.needs_input_grad[1]:
                 gs = gloss.detach().float().reshape(1).contiguous()
-                dz = ops.clip_dz_tc(coef_t, cz, x, z, gs) if ctx.tc else ops.clip_dz(coef, cz, x, z, gs)
+                if x.dtype == torch.bfloat16:
+                    dz = ops.clip_dz_bf16(coef, cz, x, z, gs)
+                else:
+                    dz = ops.clip_dz_tc(coef_t, cz, x, z, gs) if ctx.tc else ops.clip_dz(coef, cz, x, z, gs)
             if ctx.needs_input_grad[0]:
+                assert x.dtype == torch.float32, "speech-side gradient is not available with bf16 transport"
                 # symmetric formula for the speech side (appendix A.5); rarely needed (Y carries no grad)
                 gl = coef * logits * (xn2.sqrt()[:, None] * zn2.sqrt()[None, :]) / torch.exp(t)
                 cx = gl.sum(dim=1) / xn2
                 dx = ops.clip_dz(coef.t().contiguous(), cx.contiguous(), z, x, gloss.detach().float().reshape(1).contiguous())
             if ctx.needs_input_grad[2] and ctx.use_temp:
                 dtemp = (partial[1] * gloss).reshape(1)
-        return dx, dz, dtemp, None, None, None, None
+        return dx, dz, dtemp, None, None, None, None, None
 
 
 class CLIPLoss(nn.Module):
@@ -111,18 +127,20 @@ class CLIPLoss(nn.Module):
         xf = x.reshape(batch_size, -1).float().contiguous()
         yf = y.reshape(batch_size, -1).float().contiguous()
         group = self.process_group
+        xn2 = None
         if group is not None:
             pre = getattr(self, "_prefetched", None)
             self._prefetched = None
             if pre is not None and pre[0] == x.data_ptr() and pre[1] == tuple(x.shape):
-                pre[2].wait()                    # gather launched before the encoder forward (DataParallel.prefetch_targets)
-                xf = pre[3]
+                for work in pre[2]:
+                    work.wait()                  # gather launched before the encoder forward (DataParallel.prefetch_targets)
+                xf, xn2 = pre[3], pre[4]
             else:
-                xf = sd_dist.all_gather_rows(xf, group)
+                xf, xn2 = sd_dist.gather_speech_rows(xf, group, not x.requires_grad)
         zn2 = getattr(y, "_sd_norm2", None)      # set by BrainEncoder.forward (fused into its last epilogue)
         if zn2 is not None and (zn2.shape[0] != batch_size or y.dtype != torch.float32):
             zn2 = None
-        loss, logits = _ClipFn.apply(xf, yf, self.temp, self.reduction, bool(fast), group, zn2)
+        loss, logits = _ClipFn.apply(xf, yf, self.temp, self.reduction, bool(fast), group, zn2, xn2)
         if return_logits:
             return (logits if fast else logits.t()), loss
         return loss

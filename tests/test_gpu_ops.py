@@ -328,6 +328,34 @@ def test_clip_tensor_core_kernels(M, N, D, diag0):
     assert rel(dz, ref) < 3e-3
 
 
+@pytest.mark.parametrize("M,N,D,diag0", [(512, 256, 36864, 256), (64, 48, 4096, 0), (300, 100, 2048, 128), (2048, 256, 8192, 512),
+                                        (130, 72, 1000, 0)])
+def test_clip_bf16_transport_kernels(M, N, D, diag0):
+    """Data-parallel CLIP path: rows rounded to bf16 once (+ norms of the rounded rows), kind::f16 GEMMs.
+    The GEMMs are exact products of bf16 values accumulated in fp32, so they are checked tightly against
+    fp64 matmuls of the ROUNDED operands."""
+    ops, nat = _ops()
+    torch.manual_seed(11)
+    x = torch.randn(M, D, device=DEV)
+    z = torch.randn(N, D, device=DEV) + 0.3 * x[diag0:diag0 + N]
+    xb, xn2 = ops.cast_rows_bf16(x)
+    zb, zn2 = ops.cast_rows_bf16(z)
+    assert torch.equal(xb, x.bfloat16())
+    assert rel(xn2, (xb.double() ** 2).sum(dim=1)) < 1e-5
+    dots = ops.clip_dots(xb, zb)
+    ref = xb.double() @ zb.double().T
+    scale = float((xn2.sqrt()[:, None] * zn2.sqrt()[None, :]).max())
+    assert float((dots.double() - ref).abs().max()) / scale < 2e-6
+    coef = torch.randn(M, N, device=DEV) / M
+    cz = torch.randn(N, device=DEV) * 0.1
+    gs = torch.tensor([0.7], device=DEV)
+    dz0 = ops.clip_dz_bf16(coef, torch.zeros_like(cz), xb, z, None)          # GEMM term alone
+    assert rel(dz0, coef.bfloat16().double().T @ xb.double()) < 1e-5
+    dz = ops.clip_dz_bf16(coef, cz, xb, z, gs)
+    ref = 0.7 * (coef.bfloat16().double().T @ xb.double() - cz.double()[:, None] * z.double())
+    assert rel(dz, ref) < 1e-5
+
+
 @pytest.mark.parametrize("B,T,K,N,taps,dil,mode", [
     (100, 360, 320, 320, 3, 4, "res_stats"),      # 300 row tiles: 150 CTA pairs' worth, two column tiles
     (99, 360, 136, 640, 3, 2, "glu"),             # odd number of row tiles: the last pair has a dead half
