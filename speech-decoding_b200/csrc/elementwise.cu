@@ -142,48 +142,83 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
 }
 __device__ __forceinline__ F8 ldp8(const float* p) { return ld8<float>(p); }
 
-constexpr int RED_ROWS = 96;   // rows per block, reduction kernels (fewer blocks => fewer atomics)
-constexpr int EW_ROWS = 64;     // rows per block, pure elementwise channel kernels
+// 8 channels as loaded (bf16: one 16-byte register quad): rows waiting in flight are held packed, so that more
+// loads fit in the register budget of the HBM-bound channel kernels
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 w; };
+__device__ __forceinline__ Raw8<float> ldraw8(const float* p) {
+  Raw8<float> r;
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+  return r;
+}
+__device__ __forceinline__ Raw8<__nv_bfloat16> ldraw8(const __nv_bfloat16* p) {
+  Raw8<__nv_bfloat16> r;
+  r.w = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+__device__ __forceinline__ F8 unpack8(const Raw8<float>& r) {
+  F8 f;
+  f.v[0] = r.a.x; f.v[1] = r.a.y; f.v[2] = r.a.z; f.v[3] = r.a.w;
+  f.v[4] = r.b.x; f.v[5] = r.b.y; f.v[6] = r.b.z; f.v[7] = r.b.w;
+  return f;
+}
+__device__ __forceinline__ F8 unpack8(const Raw8<__nv_bfloat16>& r) {
+  F8 f;
+  const uint32_t w[4] = {r.w.x, r.w.y, r.w.z, r.w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    f.v[2 * i] = t.x; f.v[2 * i + 1] = t.y;
+  }
+  return f;
+}
+
 
 // MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce over g = du * gelu'(bn(y)) (g is not stored:
 // the apply pass recomputes it, which is cheaper than a 59 MB write + read)
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3)
 colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ ss, double* __restrict__ out,
                  int64_t rows, int Cp) {
   extern __shared__ float red_smem[];   // [blockDim.y][Cp] x 2
   const int cv = threadIdx.x, c = cv * 8, ry = threadIdx.y, R = blockDim.y;
-  constexpr int UNR = MODE == 0 ? 2 : 1;   // rows in flight per thread (register budget)
-  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS;
-  const int64_t r1 = min(rows, r0 + RED_ROWS);
+  constexpr int UNR = MODE == 0 ? 2 : 4;   // rows in flight per thread (held packed; register budget)
+  // persistent blocks (grid = SMs x resident blocks): groups of UNR*R rows strided over the grid -- no tail wave,
+  // and one shared-memory reduction + one round of atomics per block
+  const int64_t r1 = rows;
+  const int64_t r_stride = (int64_t)gridDim.x * UNR * R;
   F8 a, q;
 #pragma unroll
   for (int i = 0; i < 8; ++i) a.v[i] = q.v[i] = 0.f;
   F8 sc, sh;
   if (MODE == 1) { sc = ldp8(ss + c); sh = ldp8(ss + Cp + c); }
-  for (int64_t r = r0 + ry; r < r1; r += UNR * R) {
-    F8 v[UNR], yy[UNR];
+  for (int64_t r = (int64_t)blockIdx.x * UNR * R + ry; r < r1; r += r_stride) {
+    Raw8<T> rv[UNR], ry_[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int64_t rr = r + (int64_t)u * R;
       if (rr < r1) {
-        v[u] = ld8<T>(x + rr * Cp + c);
-        if (MODE == 1) yy[u] = ld8<T>(y + rr * Cp + c);
+        rv[u] = ldraw8(x + rr * Cp + c);
+        if (MODE == 1) ry_[u] = ldraw8(y + rr * Cp + c);
       }
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int64_t rr = r + (int64_t)u * R;
       if (rr >= r1) break;
+      const F8 v = unpack8(rv[u]);
       if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a.v[i] += v[u].v[i]; q.v[i] += v[u].v[i] * v[u].v[i]; }
+        for (int i = 0; i < 8; ++i) { a.v[i] += v.v[i]; q.v[i] += v.v[i] * v.v[i]; }
       } else {
+        const F8 yy = unpack8(ry_[u]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float g = v[u].v[i] * gelu_grad_t<T>(fmaf(yy[u].v[i], sc.v[i], sh.v[i]));
+          float g = v.v[i] * gelu_grad_t<T>(fmaf(yy.v[i], sc.v[i], sh.v[i]));
           a.v[i] += g;
-          q.v[i] = fmaf(g, yy[u].v[i], q.v[i]);        // sum g*y; sum g*xhat = invstd*(sum g*y - mean*sum g) is formed in fp64 later
+          q.v[i] = fmaf(g, yy.v[i], q.v[i]);        // sum g*y; sum g*xhat = invstd*(sum g*y - mean*sum g) is formed in fp64 later
         }
       }
     }
@@ -286,9 +321,9 @@ __global__ void __launch_bounds__(256, 4)
 bn_gelu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss, T* __restrict__ u_out, int64_t rows, int Cp) {
   constexpr int UNR = 2;
   const int c = threadIdx.x * 8, ry = threadIdx.y, R = blockDim.y;
-  const int64_t r0 = (int64_t)blockIdx.x * EW_ROWS, r1 = min(rows, r0 + EW_ROWS);
+  const int64_t r1 = rows, r_stride = (int64_t)gridDim.x * UNR * R;   // persistent blocks, see colreduce_kernel
   const F8 sc = ldp8(ss + c), sh = ldp8(ss + Cp + c);
-  for (int64_t r = r0 + ry; r < r1; r += UNR * R) {
+  for (int64_t r = (int64_t)blockIdx.x * UNR * R + ry; r < r1; r += r_stride) {
     F8 v[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
@@ -308,13 +343,13 @@ bn_gelu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss, T* __r
 
 // dy = scale * (g - sum_g/n - xhat * sum_gx/n)
 template <typename T>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ ss,
                     const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     int64_t rows, int64_t n_stat, float dscale, int C, int Cp, int training) {
-  constexpr int UNR = 1;
+  constexpr int UNR = 2;   // rows in flight per thread, held packed
   const int c = threadIdx.x * 8, ry = threadIdx.y, R = blockDim.y;
-  const int64_t r0 = (int64_t)blockIdx.x * EW_ROWS, r1 = min(rows, r0 + EW_ROWS);
+  const int64_t r1 = rows, r_stride = (int64_t)gridDim.x * UNR * R;   // persistent blocks, see colreduce_kernel
   if (blockIdx.x == 0) {
     const int tid = ry * blockDim.x + threadIdx.x;
     for (int ch = tid; ch < C; ch += blockDim.x * R) {
@@ -333,26 +368,28 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
     k2.v[i] = training ? -sc.v[i] * is.v[i] * sx : 0.f;
     k3.v[i] = training ? sc.v[i] * (mu.v[i] * is.v[i] * sx - sg) : 0.f;
   }
-  for (int64_t r = r0 + ry; r < r1; r += UNR * R) {
-    F8 v[UNR], yy[UNR];
+  for (int64_t r = (int64_t)blockIdx.x * UNR * R + ry; r < r1; r += r_stride) {
+    Raw8<T> rv[UNR], ry_[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int64_t rr = r + (int64_t)u * R;
       if (rr < r1) {
-        v[u] = ld8<T>(g + rr * Cp + c);
-        yy[u] = ld8<T>(y + rr * Cp + c);
+        rv[u] = ldraw8(g + rr * Cp + c);
+        ry_[u] = ldraw8(y + rr * Cp + c);
       }
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int64_t rr = r + (int64_t)u * R;
       if (rr >= r1) break;
+      F8 v = unpack8(rv[u]);
+      const F8 yy = unpack8(ry_[u]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float gg = v[u].v[i] * gelu_grad_t<T>(fmaf(yy[u].v[i], sc.v[i], sh.v[i]));
-        v[u].v[i] = training ? fmaf(sc.v[i], gg, fmaf(k2.v[i], yy[u].v[i], k3.v[i])) : sc.v[i] * gg;
+        const float gg = v.v[i] * gelu_grad_t<T>(fmaf(yy.v[i], sc.v[i], sh.v[i]));
+        v.v[i] = training ? fmaf(sc.v[i], gg, fmaf(k2.v[i], yy.v[i], k3.v[i])) : sc.v[i] * gg;
       }
-      st8<T>(g + rr * Cp + c, v[u]);
+      st8<T>(g + rr * Cp + c, v);
     }
   }
 }
@@ -449,6 +486,20 @@ static inline int ew_grid(int64_t n, int threads) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 // rows handled concurrently by one block of the channel-vector kernels (blockDim = (Cp/8, rows))
+// grid of the persistent channel kernels: every SM holds `per_sm` blocks, never more blocks than row groups
+static inline int persistent_grid(int64_t rows, int rows_per_iter, int per_sm) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int64_t groups = (rows + rows_per_iter - 1) / rows_per_iter;
+  const int64_t g = (int64_t)sms * per_sm;
+  return (int)(groups < g ? (groups > 0 ? groups : 1) : g);
+}
+
 static inline int chan_block_rows(int Cp) {
   int r = 256 / (Cp / 8);
   return r < 1 ? 1 : (r > 16 ? 16 : r);
@@ -505,7 +556,7 @@ int sd_colstats(const void* x, double* stats, int64_t rows, int Cp, int dtype, v
   SD_REQUIRE(Cp <= 2048, "sd_colstats: Cp too large");
   dim3 block(Cp / 8, chan_block_rows(Cp));
   const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
-  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 0><<<cdiv(rows, RED_ROWS), block, smem, (cudaStream_t)stream>>>((T*)x, nullptr, nullptr, stats, rows, Cp));
+  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 0><<<persistent_grid(rows, 2 * block.y, 4), block, smem, (cudaStream_t)stream>>>((T*)x, nullptr, nullptr, stats, rows, Cp));
   return check_launch("colstats");
 }
 
@@ -521,7 +572,7 @@ int sd_bn_finalize(const double* stats, int C, int Cp, int64_t n, const float* g
 int sd_bn_gelu_fwd(const void* y, const float* ss, void* u, int64_t rows, int Cp, int dtype, void* stream) {
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_gelu_fwd: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
-  DISPATCH_DTYPE(dtype, bn_gelu_fwd_kernel<T><<<cdiv(rows, EW_ROWS), block, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)u, rows, Cp));
+  DISPATCH_DTYPE(dtype, bn_gelu_fwd_kernel<T><<<persistent_grid(rows, 2 * block.y, 4), block, 0, (cudaStream_t)stream>>>((const T*)y, ss, (T*)u, rows, Cp));
   return check_launch("bn_gelu_fwd");
 }
 
@@ -530,7 +581,7 @@ int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* re
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_gelu_bwd_reduce: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
   const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
-  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1><<<cdiv(rows, RED_ROWS), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
+  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1><<<persistent_grid(rows, 4 * block.y, 3), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
   return check_launch("bn_gelu_bwd_reduce");
 }
 
@@ -538,7 +589,7 @@ int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* re
                     int64_t rows, int64_t n_stat, float dparam_scale, int C, int Cp, int training, int dtype, void* stream) {
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_bwd_apply: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<cdiv(rows, EW_ROWS), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, dparam_scale, C, Cp, training));
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<persistent_grid(rows, 2 * block.y, 3), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, dparam_scale, C, Cp, training));
   return check_launch("bn_bwd_apply");
 }
 

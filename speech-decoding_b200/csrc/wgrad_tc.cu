@@ -130,7 +130,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     int s = 0;
     uint32_t ph = 0;
     const int iters = (s_end - s_begin) * t_blocks;
+    // 16-row MMA steps of the last time block that still hold rows t < T (TMA zero-fills the rest: skip them)
+    const int k_last = (p.T - (t_blocks - 1) * BLOCK_T + 15) >> 4;
+    int tb = 0;
     for (int it = 0; it < iters; ++it) {
+      const int k_steps = tb == t_blocks - 1 ? k_last : BLOCK_T / 16;
+      if (++tb == t_blocks) tb = 0;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       if (elect_one_sync()) {
@@ -139,6 +144,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
         const uint32_t alo = smem_desc_lo(smem_base + s * p.stage_bytes, ATOM_BYTES), blo = alo + ((2 * ATOM_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < BLOCK_T / 16; ++k) {
+          if (k >= k_steps) break;
           umma_f16(tmem_base, desc64(alo + k * (2048 >> 4), dhi), desc64(blo + k * (2048 >> 4), dhi), idesc, (it | k) != 0);
           if (do_bias) umma_f16(tmem_base + BIAS_COL, desc64(alo + k * (2048 >> 4), dhi), desc64(olo, dhi), idesc_b, (it | k) != 0);
         }
@@ -296,7 +302,12 @@ conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     int s = 0;
     uint32_t ph = 0;
     const int iters = (s_end - s_begin) * t_blocks;
+    // 16-row MMA steps of the last time block that still hold rows t < T (TMA zero-fills the rest: skip them)
+    const int k_last = (p.T - (t_blocks - 1) * BLOCK_T + 15) >> 4;
+    int tb = 0;
     for (int it = 0; it < iters; ++it) {
+      const int k_steps = tb == t_blocks - 1 ? k_last : BLOCK_T / 16;
+      if (++tb == t_blocks) tb = 0;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       if (elect_one_sync()) {
@@ -304,6 +315,7 @@ conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
         const uint32_t blo = smem_desc_lo(smem_base + s * p.stage_bytes + 2 * ATOM_BYTES, (uint32_t)p.batom_bytes);
 #pragma unroll
         for (int k = 0; k < BLOCK_T / 16; ++k) {
+          if (k >= k_steps) break;
           const uint64_t ad = desc64(alo + k * (2048 >> 4), dhi);
 #pragma unroll
           for (int j = 0; j < 3; ++j)     // tap j reads x rows t + (j-1)*dil = halo-tile rows (j*dil + ...)
