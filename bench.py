@@ -106,6 +106,16 @@ class ClockSampler:
         return out
 
 
+def conv_traffic():
+    """DRAM bytes per conv_fwd_tc launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the launches of one
+    step) from the committed ncu capture of this same command; None if the capture is not there."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_conv_fwd_traffic.json")) as f:
+            return round(float(json.load(f)["dram_bytes_per_launch"]))
+    except Exception:
+        return None
+
+
 def make_args_ns():
     from oracle.restate import make_args
     return make_args(D1=CFG["D1"], D2=CFG["D2"], F_=CFG["F"], K=CFG["K"], num_subjects=CFG["S"],
@@ -271,7 +281,7 @@ def run_ours(a, rank, world, local_rank):
                 "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": round(ach / peaks["tflops"], 4), "peak_source": peaks["source"] + " bf16_tflops_sustained",
                 "avg_launch_ms": round(tot_ms / len(recs), 4), "share_of_step": round(tot_ms / nprof / ms, 3),
-                "traffic": None}
+                "traffic": conv_traffic()}
 
     # ---- end to end: pinned host inputs, H2D every step (prefetched on a copy stream), Adam, loss read-back ----
     copy_stream = torch.cuda.Stream(device=dev)
