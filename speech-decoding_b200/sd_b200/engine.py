@@ -320,7 +320,10 @@ class ConvBlockStage(Stage):
         ops.bn_gelu_bwd(du1, sv["y1"], ss[1], red[1], dg1, dbt1, D2, train, run.bn_group)
         dy1 = du1
         dw1, db1 = zl(m.conv1.weight), zl(m.conv1.bias)
-        ops.conv_wgrad(dy1, sv["u0"], dw1, K=D2, N=D2, taps=3, dil=d1, dbias=db1)
+        # bias of a conv that feeds a training-mode BatchNorm: its gradient sum_rows(dy) is identically zero (BN
+        # backward removes the per-channel mean of dy; autograd gets rounding noise) -> left at the pool's zero and
+        # the kernel skips its bias MMAs.  Eval-mode BN (running statistics) keeps the real bias gradient.
+        ops.conv_wgrad(dy1, sv["u0"], dw1, K=D2, N=D2, taps=3, dil=d1, dbias=None if train else db1)
         du0 = torch.empty_like(dy1)
         ops.conv_fwd(dy1, run.pack.wd(self.key + ".c1"), K=D2, N=D2, taps=3, dil=d1, res=dy1, out=du0)
         # bn0 + gelu
@@ -328,7 +331,7 @@ class ConvBlockStage(Stage):
         ops.bn_gelu_bwd(du0, sv["y0"], ss[0], red[0], dg0, dbt0, D2, train, run.bn_group)
         dy0 = du0
         dw0, db0 = zl(m.conv0.weight), zl(m.conv0.bias)
-        ops.conv_wgrad(dy0, sv["x"], dw0, K=Cin, N=D2, taps=3, dil=d0, dbias=db0)
+        ops.conv_wgrad(dy0, sv["x"], dw0, K=Cin, N=D2, taps=3, dil=d0, dbias=None if train else db0)
         grads.update({m.conv2.weight: dw2, m.conv2.bias: db2, m.batchnorm1.weight: dg1, m.batchnorm1.bias: dbt1,
                       m.conv1.weight: dw1, m.conv1.bias: db1, m.batchnorm0.weight: dg0, m.batchnorm0.bias: dbt0,
                       m.conv0.weight: dw0, m.conv0.bias: db0})
