@@ -214,6 +214,16 @@ int sd_clip_dots_tc_bf16(const void* x, const void* z, float* dots, void* worksp
 int sd_clip_dz_tc_bf16(const void* coef_t, const float* cz, const void* x, const float* z, float* dz,
                        const float* gscale, int M, int N, int64_t D, void* stream);
 
+/* ---- batch preprocessing ---------------------------------------------------- */
+/* Gwilliams2022Collator.forward (dataclass/gwilliams2022.py:653-661): for every (sample, channel) row of T samples
+ *   y = x - mean(x[:baseline_len])                          baseline_correction_single, utils/preproc_utils.py:128-142
+ *   out = clamp((y - median(y)) / IQR(y), +-clamp_lim)      scaleAndClamp / sklearn RobustScaler, utils/preproc_utils.py:69-90
+ * with sklearn's float64 arithmetic (numpy linear-interpolated quartiles, IQR < 10*eps -> 1) and a float32 result.
+ * x, out: (rows, T) fp32 contiguous, rows = B*C; T <= 2048; NaN-free input (the reference's nan-aware statistics are
+ * not reproduced); in place (out == x) is allowed. */
+int sd_collate_preproc(const float* x, float* out, int64_t rows, int T, int baseline_len, float clamp_lim, int clamp,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,3 +59,19 @@ def load(layout_fn):
         del sys.modules[k]
     ref_models.ch_locations_2d = layout_fn
     return ref_models, ref_loss
+
+
+def load_preproc_utils():
+    """The unmodified speech_decoding/utils/preproc_utils.py (baseline_correction_single :128-142, scaleAndClamp
+    :69-90 -- what Gwilliams2022Collator.forward calls, dataclass/gwilliams2022.py:653-661).  Its imports of
+    termcolor and omegaconf (absent in this image, unused by those two functions) are stubbed."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    _stub("termcolor", cprint=lambda *a, **k: None)
+    _stub("omegaconf", open_dict=lambda *a, **k: None)
+    import importlib.util
+    path = os.path.join(REFERENCE_ROOT, "speech_decoding", "utils", "preproc_utils.py")
+    spec = importlib.util.spec_from_file_location("_ref_preproc_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -280,3 +280,44 @@ def train_step(sd, X, Y, subject_idxs, temp, mask, reduction="mean", train=True)
     grads = {k: (t.grad if t.grad is not None else None) for k, t in leaves.items()}
     return dict(Z=Z.detach(), loss=loss.detach(), logits=logits.detach(), dZ=Z.grad,
                 grads=grads, dtemp=temp_leaf.grad)
+
+
+# ------------------------------------------------------------------------------------------------
+# the per-batch preprocessing of Gwilliams2022Collator.forward
+# (dataclass/gwilliams2022.py:653-661) = baseline_correction_single (utils/preproc_utils.py:128-142)
+# followed by scaleAndClamp (utils/preproc_utils.py:69-90: one sklearn RobustScaler per sample, fit
+# over time per channel).  The reference hands sklearn a torch tensor, which sklearn's input validation
+# converts to FLOAT64 (a torch dtype is not a numpy float dtype), so everything between the baseline
+# subtraction and the final `.to(torch.float)` is double arithmetic.  numpy restatement, checked bit for
+# bit against the unmodified functions (tests/test_oracle.py, tests/golden/collator.npz):
+#   baseline  b = mean_t(x[:L]) in float32 (torch);     y = x - b                      (float32)
+#   center    = median_t(y) in float64: middle element, or mean of the two middle ones
+#   quantiles q = a + (b - a) * g  (g < 0.5)  |  b - (b - a) * (1 - g)  (g >= 0.5), in float64, on the order
+#             statistics at floor((n-1)*p), +1 with g = frac((n-1)*p), p = 0.25 / 0.75   (numpy "linear")
+#   scale     = q75 - q25; scale < 10*eps64 -> 1                                       (sklearn _handle_zeros_in_scale)
+#   out       = float32( (y - center) / scale ) with the division in float64, then clamp to +-clamp_lim
+# ------------------------------------------------------------------------------------------------
+def collate_preproc(X, baseline_len_samp, clamp_lim, clamp=True):
+    """X: (B, C, T) float32 array/tensor -> float32 numpy array of the same shape."""
+    x = np.asarray(X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else X, dtype=np.float32)
+    n = x.shape[-1]
+    base = torch.from_numpy(x[..., :baseline_len_samp]).mean(dim=-1).numpy()          # torch float32 mean (:138)
+    y = (x - base[..., None]).astype(np.float32).astype(np.float64)
+    ys = np.sort(y, axis=-1)
+    center = ys[..., n // 2] if n % 2 else (ys[..., n // 2 - 1] + ys[..., n // 2]) / 2.0
+
+    def quantile(p):
+        v = (n - 1) * p
+        lo = int(np.floor(v))
+        g = v - lo
+        a = ys[..., lo]
+        b = ys[..., min(lo + 1, n - 1)]
+        d = b - a
+        return a + d * g if g < 0.5 else b - d * (1 - g)
+
+    scale = quantile(0.75) - quantile(0.25)
+    scale = np.where(scale < 10 * np.finfo(np.float64).eps, 1.0, scale)
+    out = ((y - center[..., None]) / scale[..., None]).astype(np.float32)
+    if clamp:
+        out = np.clip(out, -np.float32(clamp_lim), np.float32(clamp_lim))
+    return out

@@ -1,0 +1,104 @@
+// Batch preprocessing of the reference's Gwilliams2022Collator (dataclass/gwilliams2022.py:653-661), SURVEY 8(f)
+// rank 2: per (sample, channel) row of T time samples
+//   baseline_correction_single (utils/preproc_utils.py:128-142):  y = x - mean(x[:L])
+//   scaleAndClamp (utils/preproc_utils.py:69-90): sklearn RobustScaler fit over time = (y - median) / IQR with numpy's
+//   linear-interpolated quartiles, IQR < 10*eps -> 1, all in float64 (sklearn upcasts the torch tensor it is
+//   handed), rounded to float32, clamped to +-clamp_lim.
+// One warp per row: the row is sorted by a bitonic network in shared memory (T <= 2048), the three order
+// statistics are read by every lane, and the row is normalised from the original samples.  The per-element
+// division is a reciprocal multiply plus one FMA correction step in float64 (correctly rounded before the
+// final float32 rounding; the plain fp64 divide sequence is ~3x the instructions on a GPU whose fp64 pipe runs
+// at 1/64 rate).
+#include "common.cuh"
+
+namespace sd {
+namespace {
+
+constexpr int ROWS_PER_BLOCK = 8;   // one warp per row
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+collate_preproc_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows, int T, int P, int L,
+                       float clamp_lim, int clamp) {
+  extern __shared__ float sort_smem[];   // [ROWS_PER_BLOCK][P]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROWS_PER_BLOCK + warp;
+  if (row >= rows) return;               // whole warp leaves together; only __syncwarp below
+  float* s = sort_smem + (size_t)warp * P;
+  const float* xr = x + row * T;
+
+  // baseline: mean of the first L samples (float64 sum, rounded to float32 like torch's float mean up to 1 ulp)
+  double bs = 0.0;
+  for (int i = lane; i < L; i += 32) bs += (double)xr[i];
+  const float base = (float)(warp_sum_d(bs) / (double)L);
+
+  for (int i = lane; i < P; i += 32) s[i] = i < T ? xr[i] - base : __int_as_float(0x7f800000);   // +inf padding
+  __syncwarp();
+
+  // bitonic sort, ascending
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < (P >> 1); i += 32) {
+        const int lo = ((i / j) * (j << 1)) + (i % j), hi = lo + j;
+        const float a = s[lo], b = s[hi];
+        const bool up = (lo & k) == 0;
+        if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+      }
+      __syncwarp();
+    }
+  }
+
+  // order statistics (every lane computes the same scalars)
+  const double center = (T & 1) ? (double)s[T >> 1] : ((double)s[(T >> 1) - 1] + (double)s[T >> 1]) / 2.0;
+  double q[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const double v = (double)(T - 1) * (h ? 0.75 : 0.25);
+    const int lo = (int)floor(v);
+    const double g = v - (double)lo;
+    const double a = (double)s[lo], b = (double)s[min(lo + 1, T - 1)], d = b - a;
+    q[h] = g < 0.5 ? a + d * g : b - d * (1.0 - g);
+  }
+  double scale = q[1] - q[0];
+  if (scale < 10.0 * 2.220446049250313e-16) scale = 1.0;
+  const double rcp = 1.0 / scale;
+
+  float* orow = out + row * T;
+  for (int i = lane; i < T; i += 32) {
+    const double d = (double)(xr[i] - base) - center;
+    double qv = d * rcp;
+    qv = fma(fma(-qv, scale, d), rcp, qv);      // one Newton correction: d / scale correctly rounded
+    float o = (float)qv;
+    if (clamp) o = fminf(fmaxf(o, -clamp_lim), clamp_lim);
+    orow[i] = o;
+  }
+}
+
+}  // namespace
+}  // namespace sd
+
+using namespace sd;
+
+extern "C" int sd_collate_preproc(const float* x, float* out, int64_t rows, int T, int baseline_len, float clamp_lim,
+                                  int clamp, void* stream) {
+  SD_REQUIRE(x != nullptr && out != nullptr, "sd_collate_preproc: null pointer");
+  SD_REQUIRE(T >= 1 && T <= 2048, "sd_collate_preproc: T must be in [1, 2048] (got %d)", T);
+  SD_REQUIRE(baseline_len >= 1 && baseline_len <= T, "sd_collate_preproc: baseline_len must be in [1, T] (got %d)", baseline_len);
+  if (rows <= 0) return 0;
+  int P = 2;
+  while (P < T) P <<= 1;
+  const size_t smem = (size_t)ROWS_PER_BLOCK * P * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SD_CUDA(cudaFuncSetAttribute(collate_preproc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_PER_BLOCK * 2048 * 4));
+    attr_set = true;
+  }
+  collate_preproc_kernel<<<(unsigned)cdiv(rows, ROWS_PER_BLOCK), ROWS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(
+      x, out, rows, T, P, baseline_len, clamp_lim, clamp);
+  return check_launch("collate_preproc");
+}
