@@ -86,10 +86,10 @@ using namespace sd;
 
 extern "C" int sd_collate_preproc(const float* x, float* out, int64_t rows, int T, int baseline_len, float clamp_lim,
                                   int clamp, void* stream) {
-  SD_REQUIRE(x != nullptr && out != nullptr, "sd_collate_preproc: null pointer");
   SD_REQUIRE(T >= 1 && T <= 2048, "sd_collate_preproc: T must be in [1, 2048] (got %d)", T);
   SD_REQUIRE(baseline_len >= 1 && baseline_len <= T, "sd_collate_preproc: baseline_len must be in [1, T] (got %d)", baseline_len);
-  if (rows <= 0) return 0;
+  if (rows <= 0) return 0;                                         // empty batch: nothing to do
+  SD_REQUIRE(x != nullptr && out != nullptr, "sd_collate_preproc: null pointer");
   int P = 2;
   while (P < T) P <<= 1;
   const size_t smem = (size_t)ROWS_PER_BLOCK * P * sizeof(float);

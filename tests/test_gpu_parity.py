@@ -193,6 +193,14 @@ def test_cfg1_brennan_shape_vs_oracle(precision, tol_out, tol_grad):
     run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad)
 
 
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 3e-4), ("bf16", 2e-2, 4e-2)])
+def test_cfg5_long_window_vs_oracle(precision, tol_out, tol_grad):
+    """BASELINE.json configs[4] shape class: T = 1200 (10 s x 120 Hz; 10 row tiles per sample with a ragged last
+    tile, D = F*T = 153,600 for the CLIP GEMMs), reduced width so the oracle finishes in seconds."""
+    args, X, Y, ids = oracle_case(B=12, C=40, T=1200, S=5, D1=64, D2=96, Fo=128, K=8, seed=4)
+    run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad)
+
+
 @pytest.mark.parametrize("S", [27, 49])
 def test_cfg4_mixed_subjects_vs_oracle(S):
     """BASELINE.json configs[3]: uniformly drawn subject ids (some subjects absent -> grad None)."""
