@@ -53,6 +53,9 @@ int sd_abi_version(void);
 int sd_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* force a kernel family for conv/wgrad (tests compare TC against SIMT); default SD_IMPL_AUTO */
 int sd_set_impl(int impl);
+/* cap the SMs the persistent tensor-core kernels occupy (0 = all).  Data-parallel runs leave a few SMs to the
+ * concurrent NCCL kernels: a persistent grid that does not fit next to them is serialised into two waves. */
+int sd_set_sm_limit(int n);
 
 /* ---- layout conversion ------------------------------------------------------------------------ */
 /* X (B,C,T) fp32 -> (B,T,Cp) dtype, zero padded.  Replaces the implicit layout of

@@ -26,6 +26,19 @@ int check_launch(const char* what) {
 
 int current_impl() { return g_impl; }
 
+static int g_sm_limit = 0;   // 0 = no cap
+int sm_budget() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
+void set_sm_limit(int v) { g_sm_limit = v; }
+
 }  // namespace sd
 
 using namespace sd;
@@ -44,6 +57,12 @@ int sd_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (sm_count) *sm_count = p.multiProcessorCount;
   if (cc_major) *cc_major = p.major;
   if (cc_minor) *cc_minor = p.minor;
+  return 0;
+}
+
+int sd_set_sm_limit(int n) {
+  SD_REQUIRE(n >= 0, "sd_set_sm_limit: negative limit");
+  set_sm_limit(n);
   return 0;
 }
 

@@ -336,16 +336,7 @@ clip_dz_tc_kernel(const __grid_constant__ CUtensorMap tmap_ct, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-int sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sms() { return sm_budget(); }
 
 }  // namespace
 

@@ -139,6 +139,11 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // implementation selector (api.cu)
 int current_impl();
+// SMs the persistent tensor-core kernels may occupy: the device's SM count, or the cap set with sd_set_sm_limit()
+// (data-parallel runs leave a few SMs to the concurrent NCCL kernels: a persistent grid that does not fit is
+// serialised into two waves by the first SM a collective holds).
+int sm_budget();
+void set_sm_limit(int v);
 
 // ---- per-family entry points (defined in the .cu files) ------------------------------------------
 int conv_fwd_simt(const sd_conv_args& a, cudaStream_t st);

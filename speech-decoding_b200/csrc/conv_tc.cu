@@ -668,16 +668,7 @@ CUtensorMap ta_dummy() {
 int g_conv_ws = 0;   // weight-stationary pairs: measured slower than streaming pairs at the cfg2 shapes (narrower MMAs)
 int g_conv_pair = -1;   // -1: not decided yet (SD_B200_CONV_PAIR=0 disables the CTA-pair tiles)
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count() { return sm_budget(); }
 
 }  // namespace
 

@@ -467,12 +467,7 @@ static int conv_wgrad3_tc(const sd_wgrad_args& a, void* ws, size_t ws_bytes, cud
   p.n_tiles = (a.Np + BLOCK_MN - 1) / BLOCK_MN;
   p.c_tiles = (a.Kp + p.block_c - 1) / p.block_c;
   const int base_items = p.n_tiles * p.c_tiles * a.G;
-  int sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = sm_budget();
   int nsplit = a.G > 1 ? 1 : sms / base_items;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > a.B) nsplit = a.B;
@@ -546,12 +541,7 @@ int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
   p.n_tiles = (a.Np + BLOCK_MN - 1) / BLOCK_MN;
   p.c_tiles = (a.Kp + p.block_c - 1) / p.block_c;
   const int base_items = p.n_tiles * p.c_tiles * a.taps * a.G;
-  int sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = sm_budget();
   int nsplit = a.G > 1 ? 1 : sms / base_items;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > a.B) nsplit = a.B;

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sd_abi_version": [],
     "sd_device_info": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
     "sd_set_impl": [i32],
+    "sd_set_sm_limit": [i32],
     "sd_nct_to_btc": [vp, vp, i32, i32, i32, i32, i32, vp],
     "sd_btc_to_nct": [vp, vp, i32, i32, i32, i32, i32, vp],
     "sd_pack_weight": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],

@@ -123,9 +123,21 @@ class DataParallel:
     `loss` is the global-batch loss on every rank; parameter .grad's are the
     global-batch gradients (identical on every rank)."""
 
-    def __init__(self, encoder, loss_fn, group=None, sync_bn=True, host_group=None):
+    def __init__(self, encoder, loss_fn, group=None, sync_bn=True, host_group=None, reserve_sms=None):
+        """reserve_sms: SMs left free for the NCCL kernels that run concurrently with the step (speech-row gather
+        during the encoder forward, gradient all-reduces during backward).  The conv / wgrad / CLIP kernels are
+        persistent, one CTA per SM: if a collective holds even one SM, the CTAs that cannot be placed start only
+        when others finish and the launch takes two waves.  Default: SD_B200_DP_RESERVE_SMS or 0 (no cap)."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        import os
+        if reserve_sms is None:
+            reserve_sms = int(os.environ.get("SD_B200_DP_RESERVE_SMS", "0"))
+        self.reserve_sms = int(reserve_sms)
+        if self.reserve_sms > 0 and torch.cuda.is_available():
+            from . import _native as nat
+            sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            nat.call("sd_set_sm_limit", max(2, sms - self.reserve_sms))
         self.group = group if group is not None else dist.group.WORLD
         self.host_group = host_group
         if host_group is None and dist.get_backend(self.group) != "gloo":
