@@ -95,7 +95,9 @@ int sd_sa_weights_bwd(const float* dwm, const float* w_soft, const float* mask, 
                       const float* sin_T, float* dz_ri, int D1, int K2, int C, void* stream);
 
 /* ---- implicit-GEMM Conv1d: forward and data-gradient ------------------------------------------ */
-/* out[b,t,n] = act( bias[n] + res[b,t,n] + sum_j sum_k in[b, t+(j-(taps-1)/2)*dil, k] * w[g(b),j,n,k] )
+/* out[b,t,n] = act( A(n) ( bias[n] + res[b,t,n] + sum_j sum_k in[b, t+(j-(taps-1)/2)*dil, k] * w[g(b),j,n,k] ) )
+ * with A(n)(v) = affine[n]*v + affine[Np+n] when `affine` is given (eval-mode BatchNorm folded into the epilogue,
+ * SURVEY 8f rank 4), identity otherwise;
  * zero outside [0,T) ("same" padding, models.py:128-150).  With taps=1 this is the 1x1 convs
  * (models.py:97,188-189), the channel mix (models.py:65) and, with widx, the per-subject layer
  * (models.py:98-116, a grouped GEMM indexed by subject id).  dgrad is the same op on wd. */
@@ -112,6 +114,9 @@ typedef struct {
   float* rownorm2;   /* (B) or NULL: += sum over (n,t) of out^2 per sample (CLIP norm, loss.py:65) */
   int B, T, K, Kp, N, Np, taps, dil, G;
   int act, out_mode, dtype;
+  const float* affine; /* (2,Np) fp32 per-channel scale and shift applied before `act`, or NULL.  Inference only:
+                          eval-mode BatchNorm1d + GELU (models.py:158,161) fused into the conv that feeds it
+                          (tensor-core path, SD_ACT_GELU with a BTC output) */
 } sd_conv_args;
 int sd_conv_fwd(const sd_conv_args* a, void* stream);
 

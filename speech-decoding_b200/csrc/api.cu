@@ -80,6 +80,8 @@ int sd_conv_fwd(const sd_conv_args* a, void* stream) {
   SD_REQUIRE(a->dtype == SD_F32 || a->dtype == SD_BF16, "sd_conv_fwd: bad dtype");
   SD_REQUIRE(a->B > 0 && a->T > 0, "sd_conv_fwd: empty input");
   const int impl = current_impl();
+  SD_REQUIRE(a->affine == nullptr || (impl != SD_IMPL_SIMT && conv_fwd_tc_supported(*a)),
+             "sd_conv_fwd: the fused per-channel affine (eval-mode BatchNorm) needs the tensor-core path with SD_ACT_GELU and a BTC output");
   if (impl == SD_IMPL_TC) {
     SD_REQUIRE(conv_fwd_tc_supported(*a), "sd_conv_fwd: tcgen05 path does not support this configuration");
     return conv_fwd_tc(*a, (cudaStream_t)stream);

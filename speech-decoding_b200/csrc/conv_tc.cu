@@ -48,6 +48,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct FwdParams {
   const float* bias;
+  const float* affine;   // (2, Np) per-channel scale, shift before the activation (folded eval-mode BatchNorm) or null
   const __nv_bfloat16* res;
   __nv_bfloat16* out_btc;
   float* out_nct;
@@ -59,7 +60,7 @@ struct FwdParams {
   int block_n, n_tiles, m_tiles_per_sample, num_tiles, k_blocks;
   int act, out_mode, D2, Op;
   // shared-memory plan (byte offsets from the 1024-aligned base)
-  int num_mpairs, sa_slots, sw_slots, a_bytes, w_bytes, a_rows, halo, off_w, w0cols, off_stg0, off_stg1, off_stgr, off_bias, off_stats, off_bar, cols_alloc;
+  int num_mpairs, sa_slots, sw_slots, a_bytes, w_bytes, a_rows, halo, off_w, w0cols, off_stg0, off_stg1, off_stgr, off_bias, off_affine, off_stats, off_bar, cols_alloc;
 };
 
 // tensor maps of the epilogue tensors, one per column-half of the tile (the halves may differ in width)
@@ -146,6 +147,17 @@ __device__ __forceinline__ void lds16_f32_add(uint32_t saddr, float (&v)[16]) {
     v[4 * h] += f.x; v[4 * h + 1] += f.y; v[4 * h + 2] += f.z; v[4 * h + 3] += f.w;
   }
 }
+// v = v * scale + shift with 16 scales / shifts read from shared memory
+__device__ __forceinline__ void lds16_f32_affine(uint32_t s_scale, uint32_t s_shift, float (&v)[16]) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    float4 a, b;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(s_scale + 16 * h));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(s_shift + 16 * h));
+    v[4 * h] = fmaf(v[4 * h], a.x, b.x); v[4 * h + 1] = fmaf(v[4 * h + 1], a.y, b.y);
+    v[4 * h + 2] = fmaf(v[4 * h + 2], a.z, b.z); v[4 * h + 3] = fmaf(v[4 * h + 3], a.w, b.w);
+  }
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
 
 // PAIR: the two CTAs of a cluster work on two consecutive 128-row tiles of the SAME column tile as one
@@ -221,6 +233,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     if (p.stats)
       for (int i = threadIdx.x; i < 8 * p.cols_alloc; i += NUM_THREADS) s_stats[i] = 0.f;   // [quadrant][sum, sumsq][col]
+    if (p.affine) {   // scale (1 beyond Np) and shift (0 beyond Np)
+      float* s_aff = reinterpret_cast<float*>(smem_gen + p.off_affine);
+      for (int i = threadIdx.x; i < p.cols_alloc; i += NUM_THREADS) {
+        s_aff[i] = i < p.Np ? p.affine[i] : 1.f;
+        s_aff[p.cols_alloc + i] = i < p.Np ? p.affine[p.Np + i] : 0.f;
+      }
+    }
   }
   if (warp == 1) {
     if (PAIR) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
@@ -385,6 +404,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int hsel = ew >> 2;   // which half of the tile's column chunks this warp owns
     const int row = quad * 32 + lane;
     const uint32_t s_bias = smem_base + p.off_bias;
+    const uint32_t s_aff = smem_base + p.off_affine;
     float* s_stats = reinterpret_cast<float*>(smem_gen + p.off_stats);
     // chunk range [ch0, ch1) of 16-column chunks owned by this warp
     const int nch = glu ? (half_n >> 4) : (p.block_n >> 4);
@@ -474,6 +494,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
           lds16_f32_add(s_bias + nb * 4, v);
           if (p.res && live) lds16_bf16_add(myr + so, v);
+          if (p.affine) lds16_f32_affine(s_aff + nb * 4, s_aff + (p.cols_alloc + nb) * 4, v);
           if (p.act == SD_ACT_GELU) {
             if (p.preact) sts16_bf16(my0 + so, v);
 #pragma unroll
@@ -715,7 +736,8 @@ bool conv_fwd_tc_supported(const sd_conv_args& a) {
   if (a.act == SD_ACT_GLU && ((a.N / 2) % 8 != 0 || a.out_mode != SD_OUT_BTC || a.N % 2)) return false;
   if (a.stats && (a.act != SD_ACT_NONE || a.out_mode != SD_OUT_BTC)) return false;
   if (a.rownorm2 && a.out_mode != SD_OUT_NCT_F32) return false;
-  if (a.res && (a.act != SD_ACT_NONE || a.out_mode != SD_OUT_BTC)) return false;
+  if (a.res && ((a.act != SD_ACT_NONE && a.act != SD_ACT_GELU) || a.out_mode != SD_OUT_BTC)) return false;
+  if (a.affine && (a.act != SD_ACT_GELU || a.out_mode != SD_OUT_BTC || a.preact || a.stats)) return false;
   if (a.out_mode == SD_OUT_NCT_F32 && a.act != SD_ACT_GELU) return false;
   if (((uintptr_t)a.in & 15) || ((uintptr_t)a.w & 15) || ((uintptr_t)a.out & 15) || ((uintptr_t)a.res & 15) ||
       ((uintptr_t)a.preact & 15))
@@ -729,6 +751,7 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.bias = a.bias;
+  p.affine = a.affine;
   p.res = reinterpret_cast<const __nv_bfloat16*>(a.res);
   p.out_btc = reinterpret_cast<__nv_bfloat16*>(a.out);
   p.out_nct = reinterpret_cast<float*>(a.out);
@@ -777,11 +800,12 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
     w0 = (nch + 1) / 2 * 16; w1 = nch / 2 * 16;            // column widths of the two warp halves
     p.w0cols = w0;
     const bool need_stg1 = glu || (a.act == SD_ACT_GELU && a.out_mode == SD_OUT_BTC);
-    const int stg_bytes = BLOCK_M * bn * 2;
+    const int stg_bytes = (a.act == SD_ACT_GELU && a.preact == nullptr) ? 0 : BLOCK_M * bn * 2;   // GELU without a saved pre-activation stages only its output
     const int stg1_bytes = need_stg1 ? BLOCK_M * (glu ? bn / 2 : bn) * 2 : 0;
-    const int stgr_bytes = a.res ? stg_bytes : 0;
+    const int stgr_bytes = a.res ? BLOCK_M * bn * 2 : 0;
     const int stats_bytes = a.stats ? 8 * p.cols_alloc * 4 : 0;   // per TMEM quadrant: sums and sums of squares
-    const int tail = stg_bytes + stg1_bytes + stgr_bytes + (glu ? 2 : 1) * p.cols_alloc * 4 + stats_bytes + 16 + 512;
+    const int affine_bytes = a.affine ? 2 * p.cols_alloc * 4 : 0;
+    const int tail = stg_bytes + stg1_bytes + stgr_bytes + (glu ? 2 : 1) * p.cols_alloc * 4 + stats_bytes + affine_bytes + 16 + 512;
     const int ring = SMEM_LIMIT - 1024 - tail;
     int sa, sw, w_region;
     if (mode == 2) {
@@ -810,6 +834,7 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
     p.off_stgr = off; off += stgr_bytes;
     p.off_bias = off; off += (glu ? 2 : 1) * p.cols_alloc * 4;
     p.off_stats = off; off += stats_bytes;
+    p.off_affine = off; off += affine_bytes;
     off = (off + 15) / 16 * 16;
     p.off_bar = off; off += 512;
     smem_bytes = off + 1024;

@@ -20,7 +20,7 @@ class ConvArgs(C.Structure):
                 ("preact", vp), ("stats", vp), ("rownorm2", vp),
                 ("B", i32), ("T", i32), ("K", i32), ("Kp", i32), ("N", i32), ("Np", i32),
                 ("taps", i32), ("dil", i32), ("G", i32),
-                ("act", i32), ("out_mode", i32), ("dtype", i32)]
+                ("act", i32), ("out_mode", i32), ("dtype", i32), ("affine", vp)]
 
 
 class WgradArgs(C.Structure):

@@ -21,6 +21,7 @@ from . import _native as nat
 from . import ops
 from .ops import rup8
 
+FUSE_EVAL_BN = True     # inference: fold eval-mode BatchNorm + GELU into the producing conv epilogue (tests flip it)
 BN_MOMENTUM, BN_EPS = 0.1, 1e-5          # nn.BatchNorm1d defaults (models.py:135,143)
 
 
@@ -277,6 +278,23 @@ class ConvBlockStage(Stage):
         train = m.batchnorm0.training
         stats = run.scratch.take(4 * D2p).view(2, 2 * D2p) if train else None
         ss = torch.empty((2, 4 * D2p), dtype=torch.float32, device=dev)
+        if (not train and sv is None and dt == torch.bfloat16 and FUSE_EVAL_BN and D2 % 8 == 0
+                and ops.get_impl() != "simt"):        # (the fused epilogue lives in the tensor-core kernel)
+            # inference (eval mode, nothing saved for backward): BatchNorm is a per-channel affine known up front,
+            # so BN + GELU ride in the epilogue of the conv that feeds them -- no y0/y1 tensors,
+            # no separate normalisation pass
+            self._bn(run, m.batchnorm0, None, B * T, ss[0])
+            self._bn(run, m.batchnorm1, None, B * T, ss[1])
+            u0 = torch.empty((B, T, D2p), dtype=dt, device=dev)
+            ops.conv_fwd(x, run.pack.wf(self.key + ".c0"), K=Cin, N=D2, taps=3, dil=d0, bias=m.conv0.bias,
+                         res=x if m.k != 0 else None, out=u0, act=nat.ACT_GELU, affine=ss[0])
+            u1 = torch.empty_like(u0)
+            ops.conv_fwd(u0, run.pack.wf(self.key + ".c1"), K=D2, N=D2, taps=3, dil=d1, bias=m.conv1.bias, res=u0,
+                         out=u1, act=nat.ACT_GELU, affine=ss[1])
+            out = torch.empty((B, T, D2p), dtype=dt, device=dev)
+            ops.conv_fwd(u1, run.pack.wf(self.key + ".c2"), K=D2, N=2 * D2, taps=3, dil=m.conv2.dilation[0],
+                         bias=m.conv2.bias, out=out, act=nat.ACT_GLU)      # y2 is not kept either
+            return out
         y0 = torch.empty((B, T, D2p), dtype=dt, device=dev)
         ops.conv_fwd(x, run.pack.wf(self.key + ".c0"), K=Cin, N=D2, taps=3, dil=d0, bias=m.conv0.bias,
                      res=x if m.k != 0 else None, out=y0, stats=stats[0] if train else None)

@@ -28,8 +28,17 @@ def dtypes(precision=None):
     return _PRECISIONS[precision or _precision]
 
 
+_IMPL = "auto"
+
+
+def get_impl():
+    return _IMPL
+
+
 def set_impl(name: str):
     """'auto' | 'simt' | 'tc' | 'tc_1cta' | 'tc_ws' -- kernel family for conv / wgrad (tests)."""
+    global _IMPL
+    _IMPL = name
     nat.call("sd_set_impl", {"auto": nat.IMPL_AUTO, "simt": nat.IMPL_SIMT, "tc": nat.IMPL_TC, "tc_1cta": nat.IMPL_TC_1CTA,
                                 "tc_ws": nat.IMPL_TC_WS}[name])
 
@@ -95,11 +104,11 @@ def btc_to_nct(a, C):
 
 # ---- conv ----------------------------------------------------------------------------------------
 def conv_fwd(inp, w, *, K, N, taps=1, dil=1, bias=None, res=None, widx=None, G=1, out=None, preact=None,
-             stats=None, rownorm2=None, act=nat.ACT_NONE, out_mode=nat.OUT_BTC):
+             stats=None, rownorm2=None, act=nat.ACT_NONE, out_mode=nat.OUT_BTC, affine=None):
     B, T, Kp = inp.shape
     Np = rup8(N)
     a = nat.ConvArgs(_p(inp), _p(w), _p(bias), _p(res), _p(widx), _p(out), _p(preact), _p(stats), _p(rownorm2),
-                     B, T, K, Kp, N, Np, taps, dil, G, act, out_mode, code_of(inp))
+                     B, T, K, Kp, N, Np, taps, dil, G, act, out_mode, code_of(inp), _p(affine))
     nat.call("sd_conv_fwd", a, _st())
     return out
 

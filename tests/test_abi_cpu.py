@@ -42,6 +42,6 @@ def test_abi_version_and_error_string():
 
 def test_struct_layout_matches_c():
     # sizeof() as the C compiler lays the structs out (9 pointers + 12 ints; 6 pointers + 9 ints + 4 i64 + int)
-    assert ctypes.sizeof(_native.ConvArgs) == 9 * 8 + 12 * 4
+    assert ctypes.sizeof(_native.ConvArgs) == 9 * 8 + 12 * 4 + 8      # + the trailing `affine` pointer
     assert ctypes.sizeof(_native.WgradArgs) == 6 * 8 + 9 * 4 + 4 + 4 * 8 + 8 + 16
     assert ctypes.sizeof(_native.PackEntry) == 3 * 8 + 6 * 4

@@ -250,3 +250,37 @@ def test_cfg2_full_size_properties():
         Za = enc(X[:8], ids[:8])
         Zb = enc(X[:4], ids[:4])
     assert G.rel_err(Za[:4], Zb) < 1e-6
+
+
+def test_eval_forward_with_folded_batchnorm():
+    """Inference path: in eval mode under no_grad the bf16 engine folds BatchNorm + GELU into the
+    producing conv's epilogue.  The fused forward must agree with the unfused one (which rounds y to bf16 before the
+    normalisation) to bf16 accuracy, and with the oracle's eval forward as well as the unfused path does."""
+    import sd_b200
+    from sd_b200 import engine
+    from speech_decoding.models import BrainEncoder
+    sd_b200.set_precision("bf16")
+    args, X, Y, ids = oracle_case(B=16, C=60, T=360, S=9, D1=270, D2=320, Fo=256, K=8, seed=6)
+    enc = BrainEncoder(args).to(DEV)
+    with torch.no_grad():                                   # non-trivial running statistics and affine
+        for mod in enc.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                mod.running_mean.normal_(0, 0.3); mod.running_var.uniform_(0.5, 2.0)
+                mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.2)
+    enc.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in enc.state_dict().items()}
+    ref = restate.encoder_forward(sd, X, ids.tolist(), train=False, mask=None)
+    outs = {}
+    try:
+        for fuse in (False, True):
+            engine.FUSE_EVAL_BN = fuse
+            with torch.no_grad():
+                outs[fuse] = enc(X.to(DEV), ids).float().cpu()
+    finally:
+        engine.FUSE_EVAL_BN = True
+    e_unfused, e_fused = G.rel_l2(outs[False], ref), G.rel_l2(outs[True], ref)
+    assert G.rel_l2(outs[True], outs[False]) < 1.5e-2
+    assert e_fused < max(2e-2, 1.25 * e_unfused), (e_fused, e_unfused)
+    # eval mode with autograd on keeps the unfused (differentiable) path and still matches
+    Zg = enc(X.to(DEV), ids)
+    assert Zg.requires_grad and G.rel_l2(Zg.detach().float().cpu(), outs[False]) < 1e-6
