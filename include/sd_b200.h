@@ -222,6 +222,23 @@ int sd_clip_dots_tc_bf16(const void* x, const void* z, float* dots, void* worksp
 int sd_clip_dz_tc_bf16(const void* coef_t, const float* cz, const void* x, const float* z, float* dz,
                        const float* gscale, int M, int N, int64_t D, void* stream);
 
+/* ---- optimizer ------------------------------------------------------------------ */
+/* torch.optim.Adam over brain_encoder.parameters() + loss_func.parameters() (train.py:161-163,201-203) as ONE launch
+ * over a device table of the parameters that received a gradient (absent subjects are skipped like torch does).
+ * Per entry: step_size = lr / (1 - beta1^step), bias_correction2_sqrt = sqrt(1 - beta2^step) of THAT parameter's
+ * step count; complex parameters are passed as 2n interleaved floats.  fp32, torch's operation order. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  float step_size;
+  float bias_correction2_sqrt;
+} sd_adam_entry;
+int sd_adam_step(const sd_adam_entry* table, int n_entries, int blocks_per_entry, float beta1, float beta2, float eps,
+                 float weight_decay, void* stream);
+
 /* ---- batch preprocessing ---------------------------------------------------- */
 /* Gwilliams2022Collator.forward (dataclass/gwilliams2022.py:653-661): for every (sample, channel) row of T samples
  *   y = x - mean(x[:baseline_len])                          baseline_correction_single, utils/preproc_utils.py:128-142

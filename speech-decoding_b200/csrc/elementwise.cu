@@ -619,3 +619,38 @@ int sd_gelu_bwd(void* du_dp, const void* p, int64_t rows, int Cp, int dtype, voi
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-tensor Adam (the reference's optimizer is torch.optim.Adam over
+// brain_encoder.parameters() + loss_func.parameters(), train.py:161-163,201-203): ONE launch updates every
+// parameter that received a gradient.  Arithmetic in the order of torch's Adam (lerp, mul + addcmul,
+// sqrt / bias_correction2_sqrt + eps, addcdiv), fp32, complex parameters as interleaved real pairs.
+// ---------------------------------------------------------------------------------------------------
+namespace sd {
+__global__ void __launch_bounds__(256) adam_multi_kernel(const sd_adam_entry* __restrict__ table, float beta1, float beta2,
+                                                         float eps, float weight_decay) {
+  const sd_adam_entry e = table[blockIdx.y];
+  const float w1 = 1.0f - beta1, w2 = 1.0f - beta2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = e.grad[i];
+    const float p = e.param[i];
+    if (weight_decay != 0.f) g = fmaf(weight_decay, p, g);              // grad.add(param, alpha=weight_decay)
+    float m = e.exp_avg[i], v = e.exp_avg_sq[i];
+    m = fmaf(w1, g - m, m);                                             // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(w2 * g, g, v * beta2);                                     // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = sqrtf(v) / e.bias_correction2_sqrt + eps;
+    e.exp_avg[i] = m;
+    e.exp_avg_sq[i] = v;
+    e.param[i] = p - e.step_size * (m / denom);                         // param.addcdiv_(exp_avg, denom, -step_size)
+  }
+}
+}  // namespace sd
+
+extern "C" int sd_adam_step(const sd_adam_entry* table, int n_entries, int blocks_per_entry, float beta1, float beta2,
+                            float eps, float weight_decay, void* stream) {
+  if (n_entries <= 0) return 0;
+  SD_REQUIRE(table != nullptr && blocks_per_entry > 0, "sd_adam_step: bad table / blocks_per_entry");
+  sd::adam_multi_kernel<<<dim3(blocks_per_entry, n_entries), 256, 0, (cudaStream_t)stream>>>(table, beta1, beta2, eps,
+                                                                                             weight_decay);
+  return sd::check_launch("adam_step");
+}

@@ -23,6 +23,11 @@ class ConvArgs(C.Structure):
                 ("act", i32), ("out_mode", i32), ("dtype", i32), ("affine", vp)]
 
 
+class AdamEntry(C.Structure):
+    _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("n", i64),
+                ("step_size", f32), ("bias_correction2_sqrt", f32)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [("dout", vp), ("inp", vp), ("dw", vp), ("dbias", vp), ("sample_order", vp),
                 ("group_offsets", vp),
@@ -68,6 +73,7 @@ SIGNATURES = {
     "sd_clip_dots_tc": [vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_dz_tc": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_collate_preproc": [vp, vp, i64, i32, i32, C.c_float, i32, vp],
+    "sd_adam_step": [vp, i32, i32, f32, f32, f32, f32, vp],
     "sd_cast_rows_bf16": [vp, vp, vp, i32, i64, vp],
     "sd_clip_coef_t_bf16": [vp, vp, i32, i32, i32, vp],
     "sd_clip_dots_tc_bf16": [vp, vp, vp, vp, i32, i32, i64, vp],
