@@ -219,6 +219,14 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
     fence_barrier_init();
   }
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream;
+  // from here on we read what it wrote (activations, BatchNorm scale/shift) -- and let our successor start its prologue
+  grid_dep_launch();
+  grid_dep_wait();
   // bias (zero beyond N) and statistics accumulators in shared memory
   {
     float* s_bias = reinterpret_cast<float*>(smem_gen + p.off_bias);
@@ -240,10 +248,6 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         s_aff[p.cols_alloc + i] = i < p.Np ? p.affine[p.Np + i] : 0.f;
       }
     }
-  }
-  if (warp == 1) {
-    if (PAIR) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
-    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / multicast commit
@@ -918,29 +922,23 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   const KernelFn kernel = kernels[mode][a.taps == 3];
   if (pair) {
     int grid = 2 * (p.num_tiles < n_pairs ? p.num_tiles : n_pairs);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
     static int max_pairs = -1;
     if (max_pairs < 0) {   // all pairs must be co-resident: the tile walk is statically strided
-      cudaLaunchConfig_t q = cfg;
-      q.dynamicSmemBytes = SMEM_LIMIT;
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(grid); q.blockDim = dim3(NUM_THREADS); q.dynamicSmemBytes = SMEM_LIMIT; q.stream = st;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+      q.attrs = &attr; q.numAttrs = 1;
       SD_CUDA(cudaOccupancyMaxActiveClusters(&max_pairs, kernels[1][1], &q));
     }
-    if (2 * max_pairs < grid) { grid = 2 * max_pairs; cfg.gridDim = dim3(grid); }
+    if (2 * max_pairs < grid) grid = 2 * max_pairs;
     SD_REQUIRE(grid >= 2 && (mode != 2 || grid / 2 >= p.n_tiles), "conv_fwd_tc: not enough resident CTA pairs (%d)", grid / 2);
-    SD_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tw, em, p));
+    SD_CUDA(launch_pdl(kernel, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, st, 2, ta, tw, em, p));
   } else {
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(ta, tw, em, p);
+    SD_CUDA(launch_pdl(kernel, dim3(grid), dim3(NUM_THREADS), (size_t)smem_bytes, st, 1, ta, tw, em, p));
   }
   return check_launch("conv_fwd_tc");
 }

@@ -100,6 +100,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   }
 }
 
+// ---- device: programmatic dependent launch ----------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining: it runs its prologue (barrier init, TMEM allocation, descriptor prefetch) and must call
+// grid_dep_wait() before it touches anything the predecessor wrote.  grid_dep_launch() in the predecessor lets the
+// successor's CTAs be scheduled as soon as SMs free up.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- device: TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

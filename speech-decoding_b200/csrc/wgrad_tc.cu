@@ -94,6 +94,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  grid_dep_launch();   // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  grid_dep_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -267,6 +269,8 @@ conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  grid_dep_launch();   // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  grid_dep_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -509,7 +513,7 @@ static int conv_wgrad3_tc(const sd_wgrad_args& a, void* ws, size_t ws_bytes, cud
         return 1;
     }
   }
-  conv_wgrad3_tc_kernel<<<base_items * nsplit, NUM_THREADS, smem_bytes, st>>>(tdy, tx, wm, p);
+  SD_CUDA(launch_pdl(conv_wgrad3_tc_kernel, dim3(base_items * nsplit), dim3(NUM_THREADS), (size_t)smem_bytes, st, 1, tdy, tx, wm, p));
   if (check_launch("conv_wgrad3_tc")) return 1;
   if (use_ws) {
     wgrad_reduce_kernel<<<dim3(cdiv(a.K, 128), a.N, 3), 128, 0, st>>>(p.ws, p.ws_bias, a.dw, a.dbias, a.N, a.K, 3, p.n_tiles * BLOCK_MN,
@@ -567,7 +571,7 @@ int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
   const bool use_ws = need > 0 && ws != nullptr && ws_bytes >= need && a.G == 1;
   p.ws = use_ws ? reinterpret_cast<float*>(ws) : nullptr;
   p.ws_bias = (use_ws && a.dbias) ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + bias_off) : nullptr;
-  conv_wgrad_tc_kernel<<<base_items * nsplit, NUM_THREADS, smem_bytes, st>>>(tdy, tx, p);
+  SD_CUDA(launch_pdl(conv_wgrad_tc_kernel, dim3(base_items * nsplit), dim3(NUM_THREADS), (size_t)smem_bytes, st, 1, tdy, tx, p));
   if (check_launch("conv_wgrad_tc")) return 1;
   if (use_ws) {
     wgrad_reduce_kernel<<<dim3(cdiv(a.K, 128), a.N, a.taps), 128, 0, st>>>(p.ws, p.ws_bias, a.dw, a.dbias, a.N, a.K, a.taps,
