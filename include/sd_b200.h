@@ -84,7 +84,7 @@ int sd_pack_weights(const sd_pack_entry* table, int n, int max_tiles, void* stre
  * channel mix uses (dropping input channels == zeroing weight columns).
  *   z_ri (D1,K2,2) interleaved re/im; cos,sin (K2,C); mask (C) or NULL (eval)
  *   w_soft (D1,C) fp32 saved for backward; w_packed (1,D1p,Cp) `dtype` for sd_conv_fwd. */
-#define SD_SA_MPARTS 8 /* frequency partitions of the logits kernel; scratch = SD_SA_MPARTS*D1*C floats */
+#define SD_SA_MPARTS 32 /* frequency partitions of the logits kernel; scratch = SD_SA_MPARTS*D1*C floats */
 int sd_sa_weights_fwd(const float* z_ri, const float* cos_t, const float* sin_t, const float* mask,
                       float* w_soft, void* w_packed, float* scratch, int D1, int K2, int C, int D1p, int Cp,
                       int dtype, void* stream);

@@ -13,6 +13,8 @@ namespace sd {
 
 constexpr int SA_DT = 16;     // rows of z (output channels d) per block
 constexpr int SA_MC = 128;    // frequencies per shared-memory chunk
+constexpr int SA_BWD_DT = 8;  // rows of z per block, backward (more, smaller blocks: the kernel is latency-bound)
+constexpr int SA_BWD_M = 128; // frequencies (threads) per block, backward
 
 // Partial logits: part[mp][d][c] = sum_{m in partition mp} Re z[d,m] cos[m,c] + Im z[d,m] sin[m,c].
 // A block owns SA_DT rows of z and one partition of the K^2 frequencies: every table element it reads
@@ -39,6 +41,7 @@ sa_logits_kernel(const float* __restrict__ z_ri, const float* __restrict__ cos_t
       }
       __syncthreads();
       if (c < C) {
+#pragma unroll 4
         for (int m = 0; m < mn; ++m) {
           const float cv = cos_t[(size_t)(mc + m) * C + c], sv = sin_t[(size_t)(mc + m) * C + c];
           const float4* zr = reinterpret_cast<const float4*>(&zs[m][0]);
@@ -107,16 +110,16 @@ sa_softmax_kernel(const float* __restrict__ part, const float* __restrict__ mask
 }
 
 // dw~ -> da (softmax backward through the mask) -> z.grad = da·cos^T + i da·sin^T   (appendix A.1)
-// Block = SA_DT rows d x 256 frequencies m; thread = frequency m with 2*SA_DT accumulators; the tables are
+// Block = SA_BWD_DT rows d x SA_BWD_M frequencies m; thread = frequency m with 2*SA_BWD_DT accumulators; the tables are
 // read through their TRANSPOSES (C, K^2) so that lanes (consecutive m) are coalesced; da is a smem broadcast.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SA_BWD_M)
 sa_weights_bwd_kernel(const float* __restrict__ dwm, const float* __restrict__ w_soft, const float* __restrict__ mask,
                       const float* __restrict__ cosT, const float* __restrict__ sinT, float* __restrict__ dz_ri,
                       int D1, int K2, int C) {
-  extern __shared__ float da[];  // [SA_DT][C]
-  const int d0 = blockIdx.x * SA_DT, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ float da[];  // [SA_BWD_DT][C]
+  const int d0 = blockIdx.x * SA_BWD_DT, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // softmax backward per row: da = w * (g - sum(g*w)), g = dwm * mask    (one warp per row, 2 rows per warp)
-  for (int dd = warp; dd < SA_DT; dd += 8) {
+  for (int dd = warp; dd < SA_BWD_DT; dd += SA_BWD_M / 32) {
     const int d = d0 + dd;
     float dot = 0.f;
     if (d < D1)
@@ -129,22 +132,23 @@ sa_weights_bwd_kernel(const float* __restrict__ dwm, const float* __restrict__ w
     }
   }
   __syncthreads();
-  const int m = blockIdx.y * 256 + tid;
+  const int m = blockIdx.y * SA_BWD_M + tid;
   if (m >= K2) return;
-  float re[SA_DT], im[SA_DT];
+  float re[SA_BWD_DT], im[SA_BWD_DT];
 #pragma unroll
-  for (int i = 0; i < SA_DT; ++i) re[i] = im[i] = 0.f;
+  for (int i = 0; i < SA_BWD_DT; ++i) re[i] = im[i] = 0.f;
+#pragma unroll 4
   for (int c = 0; c < C; ++c) {
     const float cv = cosT[(size_t)c * K2 + m], sv = sinT[(size_t)c * K2 + m];
 #pragma unroll
-    for (int i = 0; i < SA_DT; ++i) {
+    for (int i = 0; i < SA_BWD_DT; ++i) {
       const float a = da[i * C + c];
       re[i] = fmaf(a, cv, re[i]);
       im[i] = fmaf(a, sv, im[i]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < SA_DT; ++i)
+  for (int i = 0; i < SA_BWD_DT; ++i)
     if (d0 + i < D1) *reinterpret_cast<float2*>(dz_ri + ((size_t)(d0 + i) * K2 + m) * 2) = make_float2(re[i], im[i]);
 }
 
@@ -175,9 +179,9 @@ int sd_sa_weights_fwd(const float* z_ri, const float* cos_t, const float* sin_t,
 
 int sd_sa_weights_bwd(const float* dwm, const float* w_soft, const float* mask, const float* cos_T, const float* sin_T,
                       float* dz_ri, int D1, int K2, int C, void* stream) {
-  const size_t smem = (size_t)SA_DT * C * sizeof(float);
+  const size_t smem = (size_t)SA_BWD_DT * C * sizeof(float);
   SD_REQUIRE(smem <= 48 * 1024, "sd_sa_weights_bwd: too many sensors");
-  sa_weights_bwd_kernel<<<dim3(cdiv(D1, SA_DT), cdiv(K2, 256)), 256, smem, (cudaStream_t)stream>>>(dwm, w_soft, mask, cos_T, sin_T,
+  sa_weights_bwd_kernel<<<dim3(cdiv(D1, SA_BWD_DT), cdiv(K2, SA_BWD_M)), SA_BWD_M, smem, (cudaStream_t)stream>>>(dwm, w_soft, mask, cos_T, sin_T,
                                                                                                   dz_ri, D1, K2, C);
   return check_launch("sa_weights_bwd");
 }

@@ -419,6 +419,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, const float* _
   const int n = blockIdx.y, j = blockIdx.z;
   if (c < K) {
     float acc = 0.f;
+#pragma unroll 8
     for (int s = 0; s < nsplit; ++s) acc += ws[(((size_t)s * taps + j) * wrows + n) * wcols + c];
     dw[(long long)n * sn + (long long)c * sk + (long long)j * sj] += acc;
   }

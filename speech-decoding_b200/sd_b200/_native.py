@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsd_b200.so")
 SD_F32, SD_BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_GLU = 0, 1, 2
 OUT_BTC, OUT_NCT_F32 = 0, 1
+SA_MPARTS = 32          # SD_SA_MPARTS
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_1CTA, IMPL_TC_WS = 0, 1, 2, 3, 4
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float

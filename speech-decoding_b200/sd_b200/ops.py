@@ -185,7 +185,7 @@ def sa_weights_fwd(z_ri, cos, sin, mask, D1, K2, C, dtype):
     D1p, Cp = rup8(D1), rup8(C)
     w_soft = torch.empty((D1, C), dtype=torch.float32, device=z_ri.device)
     w_packed = torch.empty((1, 1, D1p, Cp), dtype=dtype, device=z_ri.device)
-    scratch = torch.empty((8, D1, C), dtype=torch.float32, device=z_ri.device)      # SD_SA_MPARTS partial logits
+    scratch = torch.empty((nat.SA_MPARTS, D1, C), dtype=torch.float32, device=z_ri.device)      # SD_SA_MPARTS partial logits
     nat.call("sd_sa_weights_fwd", _p(z_ri), _p(cos), _p(sin), _p(mask), _p(w_soft), _p(w_packed), _p(scratch),
              D1, K2, C, D1p, Cp, code_of(w_packed), _st())
     return w_soft, w_packed
