@@ -57,6 +57,14 @@ def _worker(rank, world, port, tmp):
     y_loc, z_loc = Yg[rank * B:(rank + 1) * B].contiguous(), Zg[rank * B:(rank + 1) * B].contiguous()
     x_all = sd.all_gather_rows(y_loc, group)
     assert torch.equal(x_all, Yg)
+    # the speech-row gather used by CLIPLoss / DataParallel.prefetch_targets: CPU tensors (and the fp32 mode) take the
+    # exact fp32 path (no bf16 transport, no norms); the asynchronous form returns the works to wait on
+    rows, norms = sd.gather_speech_rows(y_loc, group)
+    assert norms is None and torch.equal(rows, Yg)
+    rows, norms, works, _keep = sd.gather_speech_rows(y_loc, group, async_op=True)
+    for w in works:
+        w.wait()
+    assert norms is None and torch.equal(rows, Yg)
     logits, row_stat, col_lse, xn2, zn2 = _phase1(x_all, z_loc, temp)
     row_stat = sd.merge_row_stats(row_stat, group)
     row_lse = row_stat[:, 0] + torch.log(row_stat[:, 1])
