@@ -76,3 +76,31 @@ def test_same_seed_same_initialisation_as_reference():
     for k in ref:
         a, b = ref[k], mine[k]
         assert torch.equal(torch.view_as_real(a) if a.is_complex() else a, torch.view_as_real(b) if b.is_complex() else b), k
+
+
+def test_next_row_helpers_refuse_cpu_and_keep_the_reference_contracts():
+    """the GPU collator mirrors Gwilliams2022Collator's constructor fields
+    (dataclass/gwilliams2022.py:645-651) and the one-launch Adam mirrors torch.optim.Adam's constructor and
+    state layout; neither has a CPU path."""
+    from sd_b200.preproc import GpuCollator, baseline_scale_clamp
+    from sd_b200.optim import FusedAdam
+
+    class A:
+        preprocs = {"brain_resample_rate": 120, "baseline_len_sec": 0.5, "clamp": True, "clamp_lim": 20}
+    c = GpuCollator(A(), device="cpu")
+    assert (c.baseline_len_samp, c.clamp, c.clamp_lim, c.brain_resample_rate) == (60, True, 20, 120)
+    with pytest.raises(RuntimeError):
+        baseline_scale_clamp(torch.zeros(2, 3, 16), 4)
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = FusedAdam([p], lr=1e-3, betas=(0.9, 0.99), eps=1e-7, weight_decay=0.01)
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(4))], lr=1e-3, betas=(0.9, 0.99), eps=1e-7, weight_decay=0.01)
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize"):
+        assert opt.param_groups[0][k] == ref.param_groups[0][k], k
+    opt.step()                                   # no gradients anywhere: nothing to launch, nothing raised
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        opt.step()                               # a CPU parameter with a gradient is refused
+    with pytest.raises(NotImplementedError):
+        FusedAdam([p], amsgrad=True)
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)
