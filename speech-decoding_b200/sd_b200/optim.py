@@ -21,8 +21,10 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("FusedAdam: invalid hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False,
                                       maximize=False, foreach=None, capturable=False, differentiable=False, fused=None))
-        self._host = None          # pinned staging buffer for the entry table
-        self._dev = None
+        # entry tables travel through a small ring of pinned staging buffers, each guarded by an event: the host may
+        # run several steps ahead of the GPU, and a staging buffer must not be rewritten before its copy has executed
+        self._ring = []            # [host pinned uint8, device uint8, event]
+        self._turn = 0
 
     @staticmethod
     def _real(t):
@@ -63,15 +65,24 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             k = len(entries)
             nbytes = k * ctypes.sizeof(nat.AdamEntry)
-            if self._host is None or self._host.numel() < nbytes or self._dev.device != device:
-                self._host = torch.empty(max(nbytes, 8192), dtype=torch.uint8).pin_memory()
-                self._dev = torch.empty(self._host.numel(), dtype=torch.uint8, device=device)
-            table = (nat.AdamEntry * k).from_address(self._host.data_ptr())
+            if len(self._ring) < 4:
+                self._ring.append(None)
+            self._turn = (self._turn + 1) % len(self._ring)
+            slot = self._ring[self._turn]
+            if slot is None or slot[0].numel() < nbytes or slot[1].device != device:
+                host = torch.empty(max(nbytes, 8192), dtype=torch.uint8).pin_memory()
+                slot = [host, torch.empty(host.numel(), dtype=torch.uint8, device=device), torch.cuda.Event()]
+                self._ring[self._turn] = slot
+            else:
+                slot[2].synchronize()        # the copy that last used this staging buffer has executed
+            host, dev_table, event = slot
+            table = (nat.AdamEntry * k).from_address(host.data_ptr())
             for i, e in enumerate(entries):
                 table[i] = nat.AdamEntry(e[0], e[1], e[2], e[3], e[4], e[5], e[6])
             with torch.cuda.device(device), ops.stream_scope():
-                self._dev[:nbytes].copy_(self._host[:nbytes], non_blocking=True)
-                nat.call("sd_adam_step", self._dev.data_ptr(), k, min(1024, (max_n + 1023) // 1024), float(beta1), float(beta2),
+                dev_table[:nbytes].copy_(host[:nbytes], non_blocking=True)
+                event.record(torch.cuda.current_stream(device))
+                nat.call("sd_adam_step", dev_table.data_ptr(), k, min(1024, (max_n + 1023) // 1024), float(beta1), float(beta2),
                          float(group["eps"]), float(group["weight_decay"]), ops._st())
             del entries                      # (keeps contiguous grad copies alive until the launch is enqueued)
         return loss
