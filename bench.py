@@ -11,8 +11,9 @@ A step is  Z = encoder(X, ids); loss = clip(Y, Z); loss.backward()  (+ gradient 
 Prints ONE JSON line (rank 0).  See the repo-level prompt/DESIGN.md for the key meanings:
 value = samples/s with inputs resident in HBM; e2e = same through the public API from pinned host
 buffers incl. H2D copies, Adam step and the loss read-back; roofline = the tcgen05 conv kernel
-(forward + data-gradient launches) against the measured bf16 peak; cpu_baseline = the oracle
-(oracle/restate.py, the CPU restatement of the reference) on the host cores.
+(forward + data-gradient launches) against the measured bf16 peak; cpu_baseline / --impl reference =
+the reference's own unmodified modules (pip-installed under baseline/_ref, see oracle/install_reference.py;
+the oracle port oracle/restate.py only if that install is absent) on the host cores.
 """
 import argparse
 import json
@@ -122,10 +123,11 @@ def make_args_ns():
                      num_channels=CFG["C"], last4layers=True)
 
 
-def synth(B, seed, device="cpu", pin=False):
+def synth(B, seed, device="cpu", pin=False, T=None):
+    T = T or CFG["T"]
     g = torch.Generator().manual_seed(seed)
-    X = torch.randn(B, CFG["C"], CFG["T"], generator=g).clamp_(-20, 20)
-    Y = torch.randn(B, CFG["F"], CFG["T"], generator=g)
+    X = torch.randn(B, CFG["C"], T, generator=g).clamp_(-20, 20)
+    Y = torch.randn(B, CFG["F"], T, generator=g)
     ids = torch.randint(0, CFG["S"], (B,), generator=g, dtype=torch.int32)
     if pin:
         X, Y = X.pin_memory(), Y.pin_memory()
@@ -133,38 +135,120 @@ def synth(B, seed, device="cpu", pin=False):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port on the host cores
+# reference arm / cpu_baseline / stock-eager baseline: the reference's OWN modules (unmodified, pip-installed into
+# baseline/_ref by oracle/install_reference.py, loaded through oracle/ref_import.py); the oracle port
+# (oracle/restate.py) only when neither /root/reference nor baseline/_ref exists.  Never on the product path.
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(steps, warmup, sample_b=64):
-    from oracle import restate
+class ReferenceStep:
+    """One training step  Z = enc(X, ids); loss = crit(Y, Z); loss.backward()  (train.py:189-202) of the reference on
+    `device`, fp32, random-init weights of the cfg2 architecture."""
+
+    def __init__(self, device, T=None):
+        from oracle import ref_import, restate
+        self.device = torch.device(device)
+        self.args = make_args_ns()
+        self.T = T or CFG["T"]
+        torch.manual_seed(0)
+        np.random.seed(0)
+        if ref_import.available():
+            M, L = ref_import.load(lambda a: restate.synthetic_layout(a.num_channels, getattr(a, "layout_seed", 0)))
+            self.enc = M.BrainEncoder(self.args).to(self.device).train()
+            self.crit = L.CLIPLoss(self.args).to(self.device).train()
+            self.kind = "reference"
+            self.source = ("unmodified reference modules (speech_decoding/models.py, utils/loss.py) from %s"
+                           % ("baseline/_ref (pip-installed copy)" if ref_import.where() == "_ref" else "/root/reference"))
+            self.params = list(self.enc.parameters()) + list(self.crit.parameters())
+        else:
+            self.kind = "port"
+            self.source = "oracle/restate.py (CPU restatement; the reference install under baseline/_ref is absent)"
+            self.sd, loc = restate.init_state_dict(self.args, CFG["C"])
+            self.sd = {k: v.to(self.device) for k, v in self.sd.items()}
+            self.temp = torch.tensor([5.1], device=self.device)
+            self.mask = restate.dropout_mask(loc, self.args.d_drop, 7).to(self.device)
+            self.restate = restate
+
+    def data(self, B, seed=123):
+        X, Y, ids = synth(B, seed, T=self.T)
+        return X.to(self.device), Y.to(self.device), ids
+
+    def __call__(self, X, Y, ids):
+        if self.kind == "reference":
+            for p in self.params:
+                p.grad = None
+            Z = self.enc(X, ids)
+            loss = self.crit(Y, Z)
+            loss.backward()
+            return float(loss.detach())
+        return float(self.restate.train_step(self.sd, X, Y, ids.tolist(), self.temp, self.mask)["loss"])
+
+
+def cpu_reference_rate(steps, warmup, sample_b, budget_s=None):
+    """Times `warmup` + `steps` reference steps at batch `sample_b` on all host cores.  With `budget_s`, the first step is
+    used to project the run time and the batch is cut to 64 when the whole run would not fit (said in `sample`)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    args = make_args_ns()
-    sd, loc = restate.init_state_dict(args, CFG["C"])
-    X, Y, ids = synth(sample_b, 123)
-    temp = torch.tensor([5.1])
-    mask = restate.dropout_mask(loc, args.d_drop, 7)
+    ref = ReferenceStep("cpu")
+    X, Y, ids = ref.data(sample_b)
     times = []
-    for i in range(warmup + steps):
+    note = ""
+    i = 0
+    while i < warmup + steps:
         t0 = time.perf_counter()
-        restate.train_step(sd, X, Y, ids.tolist(), temp, mask)
+        ref(X, Y, ids)
         dt = time.perf_counter() - t0
+        if i == 0 and budget_s is not None and sample_b > 64 and dt * (warmup + steps) > budget_s:
+            note = " (B=%d would take %.0f s for the requested steps: sample cut to B=64)" % (sample_b, dt * (warmup + steps))
+            sample_b = 64
+            X, Y, ids = ref.data(sample_b)
+            continue
         if i >= warmup:
             times.append(dt)
+        i += 1
     ms = 1e3 * float(np.mean(times))
-    return dict(value=sample_b / (ms / 1e3), ms_per_step=ms, cores=torch.get_num_threads(), kind="port",
-                sample="oracle/restate.py fwd+bwd, fp32, B=%d of the cfg2 shapes, %d timed steps (samples/s is batch-size "
-                       "independent to first order on CPU)" % (sample_b, steps))
+    return dict(value=sample_b / (ms / 1e3), ms_per_step=ms, cores=torch.get_num_threads(), kind=ref.kind, batch=sample_b,
+                steps=len(times), warmup=warmup,
+                sample="%s; fwd + CLIP loss + backward, fp32, B=%d of the cfg2 shapes, %d warm-up + %d timed steps on %d "
+                       "threads%s" % (ref.source, sample_b, warmup, len(times), torch.get_num_threads(), note))
+
+
+def gpu_eager_rate(dev, B, steps=3, warmup=1):
+    """The reference's own modules, stock PyTorch eager (cuDNN / cuBLAS, TF32 allowed as PyTorch defaults for convs) on
+    the same GPU: the honest same-hardware competitor.  Reported next to the CPU baseline."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        ref = ReferenceStep(dev)
+        X, Y, ids = ref.data(B)
+        for _ in range(warmup):
+            ref(X, Y, ids)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ref(X, Y, ids)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": round(B / (ms / 1e3), 1), "unit": "samples/s", "ms_per_step": round(ms, 2), "kind": ref.kind,
+                "what": "%s, stock eager on this GPU, fp32 storage with TF32 tensor cores, B=%d" % (ref.source, B)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        del ref
+        torch.cuda.empty_cache()
 
 
 def run_reference(a, rank, world):
     if rank != 0:
         return
-    r = cpu_oracle_rate(max(1, min(a.steps, 3)), max(1, min(a.warmup, 1)))
+    r = cpu_reference_rate(max(1, a.steps), max(0, a.warmup), a.batch, budget_s=240.0)
     line = {"impl": "reference", "metric": "BrainEncoder+CLIP train samples/sec", "value": round(r["value"], 2),
-            "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(r["ms_per_step"], 2),
+            "unit": "samples/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": round(r["ms_per_step"], 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "cfg2 Gwilliams2022-shape (208 sensors x 360 samples, 27 subjects, D1=270 D2=320 F=1024); "
-                                   "reference CPU path = oracle port, bounded sample B=64"},
+            "config": {"workload": "cfg2 Gwilliams2022-shape MEG: B=%d, 208 sensors x 360 samples, 27 subjects, D1=270 D2=320 F=1024 "
+                                   "K=32; step = encoder fwd + CLIP loss + backward; reference CPU path (fp32, the only "
+                                   "precision the reference has) on the host cores" % r["batch"],
+                       "global_batch": r["batch"], "same_config_as_repo_arm": bool(r["batch"] == a.batch),
+                       "precision_note": "the repo arm computes in bf16 (fp32 master weights / accumulation); the reference has no bf16 path"},
             "cpu_baseline": {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
                              "sample": r["sample"]},
             "e2e": {"value": round(r["value"], 2), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -345,7 +429,7 @@ def run_ours(a, rank, world, local_rank):
     if roof:
         line["roofline"] = roof
     if world == 1 and not a.no_cpu:
-        r = cpu_oracle_rate(2, 1)
+        r = cpu_reference_rate(2, 1, 64)
         line["cpu_baseline"] = {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
                                 "sample": r["sample"]}
     print(json.dumps(line), flush=True)

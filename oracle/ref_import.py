@@ -6,21 +6,41 @@ third-party imports that are absent in this image (termcolor, mne, mne_bids)
 and a synthetic sensor layout substituted for `ch_locations_2d`
 (reference: speech_decoding/utils/layout.py:6-43 needs mne + the dataset).
 
-/root/reference exists only in the build container.  This module is used to
-  * validate oracle/restate.py (tests, CPU, when the reference is present), and
-  * generate tests/golden/*.npz (oracle/gen_golden.py).
-Nothing in the product path, the -m gpu tests, smoke() or bench.py imports it.
+/root/reference exists only in the build container; oracle/install_reference.py pip-installs the same unmodified
+package into baseline/_ref/ (git-ignored, travels to the GPU box with the snapshot).  This module is used to
+  * validate oracle/restate.py (tests, CPU, when the reference is present),
+  * generate tests/golden/*.npz (oracle/gen_golden.py), and
+  * give bench.py its reference arm / cpu_baseline / stock-eager baseline (the reference's own modules, timed --
+    never on the product path; bench.py falls back to the oracle port when neither location exists).
+Nothing in the product path, the -m gpu tests or smoke() imports it.
 """
 import importlib
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SD_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get("SD_REFERENCE_ROOT", "/root/reference"),
+               os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+
+
+def _find():
+    for c in _CANDIDATES:
+        if os.path.isfile(os.path.join(c, "speech_decoding", "models.py")):
+            return c
+    return _CANDIDATES[0]
+
+
+REFERENCE_ROOT = _find()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "speech_decoding", "models.py"))
+
+
+def where() -> str:
+    """'reference' (the mounted tree) or '_ref' (the pip-installed copy under baseline/_ref)."""
+    return "_ref" if REFERENCE_ROOT.endswith(os.path.join("baseline", "_ref")) else "reference"
 
 
 def _stub(name, **attrs):

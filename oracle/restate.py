@@ -165,11 +165,11 @@ def classifier(Z, Y):
     y = Y.reshape(B, -1).double()
     den = torch.clamp(x.norm(dim=1)[:, None] * y.norm(dim=1)[None, :], min=1e-8)
     sim = ((x @ y.T) / den).float().T
-    diags = torch.arange(B)
+    diags = torch.arange(B, device=sim.device)
     top1 = (sim.argmax(dim=1) == diags).float().mean().item()
     k = min(10, B)
     top10_idx = torch.topk(sim, k, dim=1, largest=True)[1]
-    top10 = float(np.mean([int(l) in row.tolist() for row, l in zip(top10_idx, diags)]))
+    top10 = float((top10_idx == diags[:, None]).any(dim=1).float().mean())
     return top1, top10, top10_idx, sim
 
 

@@ -39,3 +39,15 @@ def _exact_fp32_reference():
     except Exception:
         pass
     yield
+
+
+# ---- measured parity margins ------------------------------------------------------------------------------
+# Every parity test records the worst error it measured (and the tolerance it was held to) through
+# tests.parity_log.record(); at session end the table is written to gpurun_out/parity.json (when that directory
+# exists, i.e. on the GPU box) so the measured margins -- not only pass/fail -- are committed under profiles/.
+def pytest_sessionfinish(session, exitstatus):
+    try:
+        from tests import parity_log
+        parity_log.dump(os.path.join(ROOT, "gpurun_out"))
+    except Exception:
+        pass
