@@ -249,6 +249,20 @@ int sd_adam_step(const sd_adam_entry* table, int n_entries, int blocks_per_entry
 int sd_collate_preproc(const float* x, float* out, int64_t rows, int T, int baseline_len, float clamp_lim, int clamp,
                        void* stream);
 
+/* ---- peer memory for the data-parallel exchange (the reference is single-device, train.py:31) ---- */
+/* The speech rows of every rank must reach every other rank before the CLIP GEMMs (loss.py:64-68 over the global batch).
+ * Each rank owns a receive buffer allocated by sd_peer_alloc (plain cudaMalloc: it has a CUDA IPC handle -- the one
+ * allocation of this library that outlives a call, owned by the Python PeerGather object and released by sd_peer_free),
+ * peers map it with sd_ipc_open_handle and push their rows with sd_memcpy_async: a copy-engine transfer over NVLink that
+ * occupies no SM.  Handles are cudaIpcMemHandle_t blobs of sd_ipc_handle_bytes() bytes exchanged by the host. */
+int sd_peer_alloc(void** ptr, int64_t bytes);
+int sd_peer_free(void* ptr);
+int sd_ipc_handle_bytes(void);
+int sd_ipc_get_handle(void* ptr, void* handle_out);
+int sd_ipc_open_handle(const void* handle, void** ptr_out);
+int sd_ipc_close_handle(void* ptr);
+int sd_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,55 @@
+// Peer-memory plumbing for the data-parallel exchange of the speech rows: each rank owns a receive
+// buffer allocated here (cudaMalloc, so that it has a CUDA IPC handle), every other rank maps it through the handle
+// and PUSHES its rows into its slot with cudaMemcpyAsync -- the transfer runs on the copy engines over NVLink and
+// occupies no SM, so it overlaps the persistent tcgen05 grids of the encoder forward without stealing an SM from
+// them (an SM-resident NCCL all-gather kernel next to a 148-CTA persistent grid costs that grid a second wave).
+// The reference is single-device (train.py:31); this is the build's batch-sharding addition.
+#include "common.cuh"
+
+using namespace sd;
+
+extern "C" {
+
+int sd_peer_alloc(void** ptr, int64_t bytes) {
+  SD_REQUIRE(ptr != nullptr && bytes > 0, "sd_peer_alloc: bad arguments");
+  SD_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  return 0;
+}
+
+int sd_peer_free(void* ptr) {
+  if (ptr) SD_CUDA(cudaFree(ptr));
+  return 0;
+}
+
+int sd_ipc_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int sd_ipc_get_handle(void* ptr, void* handle_out) {
+  SD_REQUIRE(ptr && handle_out, "sd_ipc_get_handle: null argument");
+  cudaIpcMemHandle_t h;
+  SD_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int sd_ipc_open_handle(const void* handle, void** ptr_out) {
+  SD_REQUIRE(handle && ptr_out, "sd_ipc_open_handle: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  SD_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int sd_ipc_close_handle(void* ptr) {
+  if (ptr) SD_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+// dst / src may live on different devices (unified addressing): copy-engine transfer, asynchronous on `stream`
+int sd_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  SD_REQUIRE(dst && src && bytes >= 0, "sd_memcpy_async: bad arguments");
+  if (bytes == 0) return 0;
+  SD_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"

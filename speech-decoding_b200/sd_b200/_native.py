@@ -80,6 +80,13 @@ SIGNATURES = {
     "sd_clip_dots_tc_bf16": [vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_dz_tc_bf16": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_dz": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
+    "sd_peer_alloc": [C.POINTER(vp), i64],
+    "sd_peer_free": [vp],
+    "sd_ipc_handle_bytes": [],
+    "sd_ipc_get_handle": [vp, vp],
+    "sd_ipc_open_handle": [vp, C.POINTER(vp)],
+    "sd_ipc_close_handle": [vp],
+    "sd_memcpy_async": [vp, vp, i64, vp],
 }
 
 _lib = None
@@ -99,7 +106,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = i64 if name == "sd_clip_dots_workspace_bytes" else i32
+            fn.restype = i64 if name == "sd_clip_dots_workspace_bytes" else i32       # (sd_ipc_handle_bytes returns the size)
         _lib = l
     return _lib
 

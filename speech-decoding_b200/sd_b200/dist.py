@@ -39,6 +39,113 @@ def all_gather_rows(x, group):
     return out
 
 
+class _RawDeviceBuffer:
+    """zero-copy view of a raw device allocation for torch.as_tensor (CUDA array interface)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+class PeerGather:
+    """All-gather of the bf16 speech rows on the COPY ENGINES: every rank owns a receive buffer (two parity slots of
+    world x rows x D bf16, allocated by the native library so that it has a CUDA IPC handle), peers map it once and each
+    step PUSH their rows into their slot with peer cudaMemcpyAsync on side streams.  No SM is occupied, so the transfer
+    overlaps the persistent tcgen05 grids of the encoder forward without costing them a wave (an NCCL all-gather kernel
+    holds SMs for the whole 1.3 GB transfer at 8 GPUs).  The tiny NCCL all-gather of the row norms that follows the
+    pushes in stream order is also the arrival fence: when it completes on a rank, every peer's push has landed.
+    Slot reuse is safe with two slots because consecutive steps are separated by a collective every rank takes part in
+    (row-statistics all-reduce in the loss, gradient all-reduce in backward)."""
+
+    NSTREAMS = 4
+
+    def __init__(self, group, host_group, device):
+        self.group, self.host_group, self.device = group, host_group, torch.device(device)
+        self.world, self.rank = world_rank(group)
+        self.shape = None
+        self.base = None             # own receive buffer (device pointer)
+        self.peers = None            # device pointers of every rank's receive buffer, mapped into this process
+        self.step = 0
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.NSTREAMS)]
+        self.events = [torch.cuda.Event() for _ in range(self.NSTREAMS)]
+        self.ready = torch.cuda.Event()
+
+    def _release(self):
+        from . import _native as nat
+        if self.peers is not None:
+            for r, p in enumerate(self.peers):
+                if r != self.rank and p:
+                    nat.call("sd_ipc_close_handle", p)
+        if self.base:
+            nat.call("sd_peer_free", self.base)
+        self.base = self.peers = self.shape = None
+
+    def _setup(self, rows, D):
+        import ctypes
+        from . import _native as nat
+        torch.cuda.synchronize(self.device)
+        self._release()
+        self.slot_bytes = self.world * rows * D * 2
+        base = ctypes.c_void_p()
+        nat.call("sd_peer_alloc", ctypes.byref(base), 2 * self.slot_bytes)
+        self.base = base.value
+        hb = ctypes.create_string_buffer(nat.lib().sd_ipc_handle_bytes())
+        nat.call("sd_ipc_get_handle", self.base, hb)
+        mine = (rows, D, hb.raw)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.host_group)
+        for r, (r_rows, r_D, _) in enumerate(everyone):
+            if (r_rows, r_D) != (rows, D):
+                raise RuntimeError("sd_b200 DataParallel: rank %d holds %d x %d speech rows, rank %d holds %d x %d -- the "
+                                   "batch must be sharded evenly" % (self.rank, rows, D, r, r_rows, r_D))
+        self.peers = []
+        for r, (_, _, h) in enumerate(everyone):
+            if r == self.rank:
+                self.peers.append(self.base)
+            else:
+                out = ctypes.c_void_p()
+                nat.call("sd_ipc_open_handle", ctypes.create_string_buffer(h, len(h)), ctypes.byref(out))
+                self.peers.append(out.value)
+        flat = torch.as_tensor(_RawDeviceBuffer(self.base, 2 * self.slot_bytes), device=self.device)
+        self.slots = [flat[i * self.slot_bytes:(i + 1) * self.slot_bytes].view(torch.bfloat16).view(self.world * rows, D)
+                      for i in range(2)]
+        self.shape = (rows, D)
+        dist.barrier(group=self.host_group)     # nobody pushes before everybody has mapped
+
+    def gather(self, xb, n2):
+        """xb (rows, D) bf16, n2 (rows,) fp32, both produced on the current stream -> (all rows, all norms, works)."""
+        from . import _native as nat
+        rows, D = xb.shape
+        if self.shape != (rows, D):
+            self._setup(rows, D)
+        slot = self.step & 1
+        self.step += 1
+        nbytes = rows * D * 2
+        off = slot * self.slot_bytes + self.rank * nbytes
+        self.ready.record()
+        for k in range(self.world):               # k = 0 is the local slot; peers in ring order so that no two ranks
+            peer = (self.rank + k) % self.world   # push into the same destination at the same time
+            st = self.streams[k % self.NSTREAMS]
+            if k < self.NSTREAMS:
+                st.wait_event(self.ready)
+            nat.call("sd_memcpy_async", self.peers[peer] + off, xb.data_ptr(), nbytes, st.cuda_stream)
+        for i in range(1, min(self.NSTREAMS, self.world)):
+            self.events[i].record(self.streams[i])
+            self.streams[0].wait_event(self.events[i])
+        norms = torch.empty((self.world * rows,), dtype=n2.dtype, device=n2.device)
+        with torch.cuda.stream(self.streams[0]):
+            work = dist.all_gather_into_tensor(norms, n2, group=self.group, async_op=True)
+        return self.slots[slot], norms, [work]
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+
+_PEER_GATHER = {}      # id(group) -> PeerGather (installed by DataParallel when the copy-engine path is usable)
+
+
 def gather_speech_rows(x2d, group, allow_bf16=True, async_op=False):
     """All-gather the speech rows of every rank.  In the bf16 mode (and when no gradient flows to them) the rows are
     rounded to bf16 ONCE on the owning rank together with their squared norms: the gather then moves, and the two
@@ -49,6 +156,15 @@ def gather_speech_rows(x2d, group, allow_bf16=True, async_op=False):
     if world > 1 and allow_bf16 and x2d.is_cuda and ops.clip_bf16_ok(x2d):
         with torch.cuda.device(x2d.device), ops.stream_scope():
             xb, n2 = ops.cast_rows_bf16(x2d)
+        pg = _PEER_GATHER.get(id(group))
+        if pg is not None:
+            with torch.cuda.device(x2d.device):
+                rows, norms, works = pg.gather(xb, n2)
+            if not async_op:
+                for w in works:
+                    w.wait()
+                return rows, norms
+            return rows, norms, works, (xb, n2)
         rows = torch.empty((world * xb.shape[0], xb.shape[1]), dtype=xb.dtype, device=xb.device)
         norms = torch.empty((world * n2.shape[0],), dtype=n2.dtype, device=n2.device)
         works.append(dist.all_gather_into_tensor(norms, n2, group=group, async_op=async_op))
@@ -83,35 +199,74 @@ def merge_row_stats(row_stat, group):
 
 def gather_host_ints(values, host_group):
     """all-gather a small int64 numpy vector over the host (gloo) side channel."""
+    return gather_host_ints_async(values, host_group)()
+
+
+def gather_host_ints_async(values, host_group):
+    """Start the all-gather of a small int64 numpy vector over the host (gloo) side channel and return a function that
+    waits for it and yields the per-rank vectors.  The encoder forward starts the exchange of the subject ids and only
+    backward (which needs the union to decide which per-subject weights get a gradient) collects it, so the host never
+    blocks in the middle of enqueueing the forward."""
     world, _ = world_rank(host_group)
-    t = torch.from_numpy(np.asarray(values, dtype=np.int64))
+    t = torch.from_numpy(np.asarray(values, dtype=np.int64).copy())
     if world == 1:
-        return [t.numpy()]
+        return lambda: [t.numpy()]
     outs = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(outs, t, group=host_group)
-    return [o.numpy() for o in outs]
+    work = dist.all_gather(outs, t, group=host_group, async_op=True)
+
+    def collect():
+        work.wait()
+        return [o.numpy() for o in outs]
+    return collect
 
 
 class GradReducer:
-    """Sums parameter gradients across ranks, stage by stage, while backward
-    is still running (hooked into engine.Pipeline)."""
+    """Sums parameter gradients across ranks while backward is still running (hooked into engine.Pipeline).  Finished
+    stages are coalesced into buckets of at least `bucket_bytes` (stages finish in reverse parameter order, so their
+    slices of the GradPool are adjacent): every all-reduce is an SM-resident NCCL kernel running next to the persistent
+    one-CTA-per-SM conv / wgrad grids, and each of them costs those grids a second wave -- few, large messages keep that
+    to a couple of launches per step.  bucket_bytes = 0: one all-reduce per stage; None: SD_B200_DP_BUCKET_MB (default
+    16 MB -> three buckets for the 37 MB of cfg2 gradients)."""
 
-    def __init__(self, group):
+    def __init__(self, group, bucket_bytes=None):
+        import os
         self.group = group
         self.pending = []
+        if bucket_bytes is None:
+            bucket_bytes = int(float(os.environ.get("SD_B200_DP_BUCKET_MB", "16")) * (1 << 20))
+        self.bucket_bytes = bucket_bytes
+        self.lo = self.hi = None
+        self.flat = None
+        self.launched = 0
+
+    def _flush(self):
+        if self.lo is None or self.hi <= self.lo:
+            self.lo = self.hi = None
+            return
+        work = dist.all_reduce(self.flat[self.lo:self.hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.pending.append(work)
+        self.launched += 1
+        self.lo = self.hi = None
 
     def stage_done(self, flat, lo, hi):
-        """All-reduce flat[lo:hi] (one stage's parameter gradients, contiguous in the GradPool --
-        absent subjects included as zeros, so the message size is the same on every rank)."""
+        """flat[lo:hi] (one stage's parameter gradients, contiguous in the GradPool -- absent subjects included as
+        zeros, so the message size is the same on every rank) is final."""
         if hi <= lo:
             return
-        work = dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self.pending.append(work)
+        if self.lo is not None and not (hi == self.lo or lo == self.hi):
+            self._flush()                      # not adjacent to the open bucket
+        self.flat = flat
+        self.lo = lo if self.lo is None else min(lo, self.lo)
+        self.hi = hi if self.hi is None else max(hi, self.hi)
+        if (self.hi - self.lo) * flat.element_size() >= self.bucket_bytes:
+            self._flush()
 
     def finish(self):
+        self._flush()
         for work in self.pending:
             work.wait()
         self.pending = []
+        self.flat = None
 
 
 class DataParallel:
@@ -123,7 +278,8 @@ class DataParallel:
     `loss` is the global-batch loss on every rank; parameter .grad's are the
     global-batch gradients (identical on every rank)."""
 
-    def __init__(self, encoder, loss_fn, group=None, sync_bn=True, host_group=None, reserve_sms=None):
+    def __init__(self, encoder, loss_fn, group=None, sync_bn=True, host_group=None, reserve_sms=None, peer_gather=None,
+                 bucket_bytes=None, broadcast=True):
         """reserve_sms: SMs left free for the NCCL kernels that run concurrently with the step (speech-row gather
         during the encoder forward, gradient all-reduces during backward).  The conv / wgrad / CLIP kernels are
         persistent, one CTA per SM: if a collective holds even one SM, the CTAs that cannot be placed start only
@@ -145,12 +301,35 @@ class DataParallel:
         elif host_group is None:
             self.host_group = self.group
         pipe = encoder.pipeline()
-        pipe.reducer = GradReducer(self.group)
+        pipe.reducer = GradReducer(self.group, bucket_bytes)
         pipe.bn_group = self.group if sync_bn else None
         pipe.host_group = self.host_group
         loss_fn.process_group = self.group
         self.loss_fn = loss_fn
         loss_fn._prefetched = None
+        self.sync_bn = bool(sync_bn)
+        if broadcast:
+            # replicas must start identical (like DDP): parameters and buffers of rank 0 win.  With sync_bn=False the
+            # BatchNorm running statistics then evolve per rank (each rank normalises with its own shard's statistics);
+            # a checkpoint holds the saving rank's -- documented, not averaged.
+            with torch.no_grad():
+                for t in list(encoder.parameters()) + list(encoder.buffers()) + list(loss_fn.parameters()):
+                    if t.is_complex():
+                        dist.broadcast(torch.view_as_real(t.data), 0, group=self.group)
+                    else:
+                        dist.broadcast(t.data, 0, group=self.group)
+        # speech-row exchange on the copy engines (CUDA IPC peer buffers) instead of an SM-resident NCCL kernel
+        if peer_gather is None:
+            peer_gather = os.environ.get("SD_B200_DP_GATHER", "peer") != "nccl"
+        self.peer = None
+        dev = next(encoder.parameters()).device
+        if peer_gather and dev.type == "cuda" and dist.get_world_size(self.group) > 1:
+            try:
+                self.peer = PeerGather(self.group, self.host_group, dev)
+                _PEER_GATHER[id(self.group)] = self.peer
+            except Exception as e:                                  # pragma: no cover
+                import warnings
+                warnings.warn("sd_b200: copy-engine peer gather unavailable (%s); using the NCCL all-gather" % e)
 
     def prefetch_targets(self, Y):
         """Start the all-gather of the speech embeddings for the coming step NOW (they are input data, known

@@ -211,10 +211,11 @@ class SubjectStage(Stage):
         ops.conv_fwd(h1, run.pack.wf(self.key + ".subj"), K=D1, N=D1, widx=widx, G=S, out=h2)
         if sv is not None:
             present = np.unique(ids)
+            collect = None
             if run.host_group is not None:       # data parallel: a subject has a gradient if ANY rank saw it
-                from . import dist as sd_dist
-                present = np.unique(np.concatenate(sd_dist.gather_host_ints(ids, run.host_group)))
-            sv.update(x=x, h1=h1, widx=widx, order=d_order, offsets=d_off, present=present)
+                from . import dist as sd_dist    # (exchange started here, collected in backward: the host never blocks)
+                collect = sd_dist.gather_host_ints_async(ids, run.host_group)
+            sv.update(x=x, h1=h1, widx=widx, order=d_order, offsets=d_off, present=present, collect=collect)
         return h2
 
     def backward(self, run, sv, dout, grads, need_dx):
@@ -223,6 +224,8 @@ class SubjectStage(Stage):
         dws = run.gpool.stacked([l.weight for l in m.subject_layer])
         ops.conv_wgrad(dout, sv["h1"], dws, K=D1, N=D1, order=sv["order"], offsets=sv["offsets"], G=S,
                        strides=(D1 * D1, D1, 1, 0))
+        if sv["collect"] is not None:
+            sv["present"] = np.unique(np.concatenate(sv["collect"]()))
         for s in sv["present"]:                      # absent subjects keep grad None
             grads[m.subject_layer[int(s)].weight] = dws[int(s)]
         dh1 = torch.empty_like(dout)

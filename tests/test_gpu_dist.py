@@ -55,10 +55,11 @@ def _worker(rank, world, port, tmp, precision):
     if rank == 0:
         mask = restate.dropout_mask(enc.subject_block.spatial_attention.spatial_dropout.loc, args.d_drop, 4)
         ref = restate.train_step(sd0, Xg, Yg, idg.tolist(), crit.temp.detach().cpu(), mask)
-        tol = 2e-4 if precision == "fp32" else 5e-2
+        tol = 1e-4 if precision == "fp32" else 5e-2
         err = G.rel_err if precision == "fp32" else G.rel_l2
-        assert G.rel_err(loss, ref["loss"]) < tol
-        assert err(Z, ref["Z"][:B]) < tol
+        measured = {"loss": G.rel_err(loss, ref["loss"]), "Z": err(Z, ref["Z"][:B]), "grad_worst": 0.0}
+        assert measured["loss"] < tol
+        assert measured["Z"] < tol
         named = dict(enc.named_parameters())
         for k, g in ref["grads"].items():
             if g is None:
@@ -69,8 +70,12 @@ def _worker(rank, world, port, tmp, precision):
             if k.endswith("bias"):
                 scale = max(scale, float(ref["grads"][k[:-4] + "weight"].abs().max()))
             e = G.rel_err(named[k].grad, g, floor=scale)
-            assert e < (5e-4 if precision == "fp32" else 1e-1), (k, e)
-        assert G.rel_err(crit.temp.grad, ref["dtemp"]) < (5e-4 if precision == "fp32" else 5e-2)
+            measured["grad_worst"] = max(measured["grad_worst"], e)
+            assert e < (1e-4 if precision == "fp32" else 1e-1), (k, e)
+        measured["grad_temp"] = G.rel_err(crit.temp.grad, ref["dtemp"])
+        assert measured["grad_temp"] < (1e-4 if precision == "fp32" else 5e-2)
+        import json
+        json.dump(measured, open(os.path.join(tmp, "measured.json"), "w"))
         sd1 = enc.state_dict()
         for k, v in sd0.items():          # sd0 now holds the oracle's updated running statistics
             if "running" in k:
@@ -86,3 +91,7 @@ def test_two_gpu_data_parallel_matches_global_batch_oracle(tmp_path, precision):
         pytest.skip("needs 2 GPUs")
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), precision), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok")
+    import json
+    from tests import parity_log as PL
+    for k, v in json.load(open(tmp_path / "measured.json")).items():
+        PL.record(k, v, 1e-4 if precision == "fp32" else (1e-1 if k == "grad_worst" else 5e-2))

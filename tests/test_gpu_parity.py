@@ -1,9 +1,12 @@
 """GPU: the drop-in modules (through the C ABI) against (a) the committed golden fixtures made from the
 unmodified reference and (b) the oracle (oracle/restate.py) at the BASELINE.json shapes.
 
-Tolerances (BASELINE.json north_star): fp32 mode -- loss and gradients within 1e-4 relative (with an
-absolute floor per layer: SURVEY appendix A.4), identical top-10 retrieval; bf16 mode -- within 2e-2
-relative on loss/Z and 5e-2 of the layer scale on gradients."""
+Tolerances (BASELINE.json north_star): fp32 mode -- Z, loss and EVERY gradient within 1e-4 relative (max-norm, with
+the layer's scale as the floor for the zero-by-construction biases of SURVEY appendix A.4), identical top-10
+retrieval rows (measured worst over all configs: 2.3e-5, profiles/r2_parity.json); bf16 mode -- loss within 2e-2;
+Z and gradients within 2e-2 / 4e-2 normwise or, where the number format itself cannot, within 1.25x of the error of
+PyTorch's own bf16 autocast of the oracle on the same inputs (measured at cfg2: ours 2.3e-2 / 2.8-4.2e-2, autocast
+6.7e-2 / 8.5-13e-2).  Every measured margin is recorded through tests/parity_log.py."""
 import numpy as np
 import pytest
 import torch
@@ -94,7 +97,7 @@ def grad_check(enc, ref_grads, absent, tol, err=G.rel_err, floor_noise=None):
 # rounding noise is several times larger than at the benchmark shapes: for them the bf16 run is a
 # sanity bound (loss within 2e-2; tensors within 3e-2 / 8e-2 normwise or 2.5x PyTorch's own bf16
 # autocast error on the same net).  The strict bf16 bar is applied at full width in the cfg1 test.
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 2e-4), ("bf16", 3e-2, 8e-2)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 1e-4), ("bf16", 3e-2, 8e-2)])
 @pytest.mark.parametrize("name", G.names())
 def test_golden_train_step(name, precision, tol_out, tol_grad, monkeypatch):
     E = err_fn(precision)
@@ -216,14 +219,14 @@ def run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad, center=3, oracl
     return worst
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 3e-4), ("bf16", 2e-2, 4e-2)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 4e-2)])
 def test_cfg1_brennan_shape_vs_oracle(precision, tol_out, tol_grad):
     """BASELINE.json configs[0]: Brennan2018-shape EEG (60 ch, 3 s, B=64), full-width model."""
     args, X, Y, ids = oracle_case(B=64, C=60, T=360, S=33, D1=270, D2=320, Fo=1024, K=32, seed=1)
     run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad)
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 3e-4), ("bf16", 2e-2, 4e-2)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 4e-2)])
 def test_cfg5_long_window_vs_oracle(precision, tol_out, tol_grad):
     """BASELINE.json configs[4] shape class: T = 1200 (10 s x 120 Hz; 10 row tiles per sample with a ragged last
     tile, D = F*T = 153,600 for the CLIP GEMMs), reduced width so the oracle finishes in seconds."""
@@ -235,7 +238,7 @@ def test_cfg5_long_window_vs_oracle(precision, tol_out, tol_grad):
 def test_cfg4_mixed_subjects_vs_oracle(S):
     """BASELINE.json configs[3]: uniformly drawn subject ids (some subjects absent -> grad None)."""
     args, X, Y, ids = oracle_case(B=32, C=208, T=120, S=S, D1=270, D2=320, Fo=256, K=8, seed=2)
-    run_vs_oracle(args, X, Y, ids, "fp32", 1e-4, 3e-4)
+    run_vs_oracle(args, X, Y, ids, "fp32", 1e-4, 1e-4)
 
 
 @pytest.mark.parametrize("kind", ["all_same", "all_different", "sorted"])
@@ -244,10 +247,10 @@ def test_cfg4_degenerate_subject_patterns(kind):
     ids = {"all_same": torch.full((B,), 5, dtype=torch.int32), "all_different": torch.randperm(S)[:B].int(),
            "sorted": torch.sort(torch.randint(0, S, (B,)))[0].int()}[kind]
     args, X, Y, _ = oracle_case(B=B, C=24, T=64, S=S, D1=40, D2=48, Fo=64, K=4, seed=3)
-    run_vs_oracle(args, X, Y, ids, "fp32", 1e-4, 3e-4)
+    run_vs_oracle(args, X, Y, ids, "fp32", 1e-4, 1e-4)
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 3e-4), ("bf16", 2e-2, 4e-2)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 4e-2)])
 def test_cfg2_full_size_vs_oracle(precision, tol_out, tol_grad):
     """BASELINE.json configs[1] AS BENCHMARKED: B=256, 208 sensors x 360 samples, 27 subjects, D1=270, D2=320, F=1024.
     Z, loss, every parameter gradient, the temperature gradient and the top-10 retrieval rows against the oracle run on
