@@ -258,6 +258,26 @@ def run_reference(a, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore its pinned-memory allocations, first touch) to the CPUs NVML reports as local to
+    GPU `index`: with 8 ranks each shipping its inputs over PCIe every step, host buffers on the wrong socket make the
+    aggregate H2D rate the bottleneck of the e2e number.  Best effort; returns the number of CPUs bound to or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(a, rank, world, local_rank):
     import torch.distributed as dist
     import sd_b200
@@ -267,6 +287,7 @@ def run_ours(a, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     sd_b200.set_precision(a.precision)
     torch.manual_seed(0)           # identical replicas on every rank
     np.random.seed(0)              # identical dropout centres on every rank
@@ -287,7 +308,10 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    steps_seen = [0]
+
     def hot_step():
+        steps_seen[0] += 1
         if dp is not None:
             dp.prefetch_targets(Y)          # Y all-gather overlaps the encoder forward
         Z = enc(X, ids)
@@ -335,7 +359,7 @@ def run_ours(a, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (tcgen05 conv fwd/dgrad), CUDA events around each launch ----
     roof = None
-    if a.precision == "bf16":
+    if a.precision in ("bf16", "tf32", "tf32x3"):
         recs = []
         orig_conv = ops.conv_fwd
 
@@ -361,11 +385,17 @@ def run_ours(a, rank, world, local_rank):
         tot_fl = sum(f for _, _, f in recs)
         peaks = measured_peaks()
         ach = tot_fl / (tot_ms / 1e3) / 1e12
-        roof = {"kernel": "conv_fwd_tc_kernel (implicit-GEMM conv forward + data-gradient, %d launches/step)" % (len(recs) // nprof),
-                "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": round(ach / peaks["tflops"], 4), "peak_source": peaks["source"] + " bf16_tflops_sustained",
+        # TF32 dense peak = half the bf16 figure (datasheet ratio 1.125 / 2.25 PF; MEASURED_PEAKS.json holds bf16 only);
+        # 3xTF32 issues three TF32 MMAs per algorithmic product
+        div = {"bf16": 1.0, "tf32": 2.0, "tf32x3": 6.0}[a.precision]
+        kname = "conv_fwd_tc_kernel" if a.precision == "bf16" else "conv_fwd_tf32_kernel"
+        roof = {"kernel": "%s (implicit-GEMM conv forward + data-gradient, %d launches/step)" % (kname, len(recs) // nprof),
+                "bound": "tensor", "achieved": round(ach, 1), "peak": round(peaks["tflops"] / div, 1), "unit": "TFLOP/s",
+                "frac": round(ach / (peaks["tflops"] / div), 4),
+                "frac_of_burst_peak": round(ach / (peaks["tflops_burst"] / div), 4),
+                "peak_source": peaks["source"] + " bf16_tflops_sustained" + ("" if div == 1.0 else " / %g (%s)" % (div, a.precision)),
                 "avg_launch_ms": round(tot_ms / len(recs), 4), "share_of_step": round(tot_ms / nprof / ms, 3),
-                "traffic": conv_traffic()}
+                "traffic": conv_traffic() if a.precision == "bf16" else None}
 
     # ---- end to end: pinned host inputs, H2D every step (prefetched on a copy stream), Adam, loss read-back ----
     copy_stream = torch.cuda.Stream(device=dev)
@@ -393,6 +423,7 @@ def run_ours(a, rank, world, local_rank):
             loss = crit(Yd, Z)
             opt.zero_grad(set_to_none=True)
             loss.backward()
+            steps_seen[0] += 1
             opt.step()
             last = loss.item()                 # D2H read of the step's result (train.py:196)
         return last
@@ -418,7 +449,11 @@ def run_ours(a, rank, world, local_rank):
             "config": {"workload": "cfg2/cfg3 Gwilliams2022-shape MEG: B=%d per GPU, 208 sensors x 360 samples, 27 subjects, "
                                    "D1=270 D2=320 F=1024 K=32; step = encoder fwd + CLIP loss + backward%s"
                                    % (B, " + grad all-reduce, global-batch CLIP negatives" if world > 1 else ""),
-                       "global_batch": world * B, "precision": a.precision + (" activations, fp32 master weights/accumulate" if a.precision == "bf16" else ""),
+                       "global_batch": world * B,
+                       "precision": a.precision + {"bf16": " activations, fp32 master weights/accumulate",
+                                                   "tf32": ": fp32 storage, tcgen05 kind::tf32 convolutions / GEMMs (the reference's cuDNN default)",
+                                                   "tf32x3": ": fp32 storage, 3xTF32 split convolutions on tcgen05 (fp32-class accuracy), fp32 CLIP",
+                                                   "fp32": ": fp32 CUDA-core kernels"}[a.precision],
                        "l2": "working set (>2 GB of activations, 454 MB of inputs) exceeds the 126 MB L2",
                        "sync_bn": bool(a.sync_bn) if world > 1 else None, "loss": round(loss_val, 4)},
             "model_tflops_per_s": round(value * gflop / 1e3, 1),
@@ -426,6 +461,12 @@ def run_ours(a, rank, world, local_rank):
                     "h2d_bytes_per_step": int(Xh.numel() * 4 + Yh.numel() * 4), "d2h_bytes_per_step": 4,
                     "includes": "H2D of X,Y from pinned memory (double-buffered), fwd, loss, backward, Adam step, loss.item()"},
             "gpu_launches": launches, "clocks": clk}
+    if dp is not None:
+        red = enc.pipeline().reducer
+        line["config"]["data_parallel"] = {
+            "speech_row_gather": "copy-engine push into CUDA-IPC peer buffers (no SM)" if dp.peer is not None else "NCCL all-gather",
+            "grad_allreduce_launches_per_step": round(red.launched / max(1, steps_seen[0]), 2),
+            "numa_bound_cpus": numa_cpus}
     if roof:
         line["roofline"] = roof
     if world == 1 and not a.no_cpu:
@@ -441,7 +482,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3", "fp32"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--sync-bn", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -33,6 +33,9 @@ extern "C" {
 
 #define SD_F32 0
 #define SD_BF16 1
+#define SD_TF32 2 /* conv / wgrad only: fp32 storage, tcgen05 kind::tf32 math (BASELINE.json configs[1] "fp32/TF32").
+                     With the *_lo operand planes given (sd_tf32_split) every product is hi*hi + hi*lo + lo*hi:
+                     3xTF32, fp32-class accuracy on the tensor cores.  Elementwise entry points take SD_F32. */
 
 #define SD_ACT_NONE 0
 #define SD_ACT_GELU 1 /* out = gelu(p); p optionally saved to `preact`           (models.py:194-195) */
@@ -117,6 +120,8 @@ typedef struct {
   const float* affine; /* (2,Np) fp32 per-channel scale and shift applied before `act`, or NULL.  Inference only:
                           eval-mode BatchNorm1d + GELU (models.py:158,161) fused into the conv that feeds it
                           (tensor-core path, SD_ACT_GELU with a BTC output) */
+  const void* in_lo;   /* SD_TF32 only, or NULL: low planes of `in` / `w` (same shapes) from sd_tf32_split; both or   */
+  const void* w_lo;    /* neither.  Given: 3xTF32 (in, w must then be the HIGH planes).                                */
 } sd_conv_args;
 int sd_conv_fwd(const sd_conv_args* a, void* stream);
 
@@ -136,8 +141,15 @@ typedef struct {
   int dtype;
   void* workspace;          /* optional scratch for split-K partials (tensor-core path); NULL => atomics */
   int64_t workspace_bytes;
+  const void* dout_lo;      /* SD_TF32 only, or NULL: low planes of dout / in (3xTF32, see sd_conv_args) */
+  const void* in_lo;
 } sd_wgrad_args;
 int sd_conv_wgrad(const sd_wgrad_args* a, void* stream);
+
+/* x (n fp32, n % 4 == 0) -> hi = x rounded to the nearest TF32 value (low 13 mantissa bits zero), lo = x - hi rounded
+ * to TF32 (|x - hi - lo| <= 2^-23 |x|).  Operand planes of the 3xTF32 conv / wgrad: what cuDNN's TF32 convolution of the reference
+ * (models.py:128-150 on a GPU) loses in one rounding is carried by the lo plane. */
+int sd_tf32_split(const float* x, float* hi, float* lo, int64_t n, void* stream);
 
 /* ---- BatchNorm1d + GELU (models.py:158,161) ----------------------------------------------------- */
 /* column sums over a (rows, Cp) BTC tensor: stats[0:Cp] += sum, stats[Cp:2Cp] += sum of squares */

@@ -48,6 +48,22 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+// A bf16 call the tcgen05 kernels cannot take (odd GLU width, misaligned pointer ...) runs on the CUDA-core kernel, which
+// is ~10x slower: never silently -- the first such call of every (entry point, shape) is reported on stderr
+// (SD_B200_STRICT_TC=1 turns the report into an error).
+static int warn_simt_fallback(const char* what, int N, int K, int taps, int act, int out_mode) {
+  static unsigned long long seen[64];
+  static int n_seen = 0;
+  const unsigned long long key = ((unsigned long long)(what[8] == 'w') << 60) ^ ((unsigned long long)N << 40) ^ ((unsigned long long)K << 20) ^
+                                 ((unsigned long long)taps << 8) ^ ((unsigned long long)act << 4) ^ (unsigned long long)out_mode;
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i] == key) return 0;
+  if (n_seen < 64) seen[n_seen++] = key;
+  fprintf(stderr, "sd_b200 WARNING: %s (bf16, N=%d K=%d taps=%d act=%d out=%d) is not supported by the tcgen05 kernels and runs on the "
+                  "CUDA-core kernel (~10x slower)\n", what, N, K, taps, act, out_mode);
+  return 0;
+}
+
 }  // namespace sd
 
 using namespace sd;
@@ -56,7 +72,7 @@ extern "C" {
 
 const char* sd_last_error(void) { return g_err; }
 
-int sd_abi_version(void) { return 1; }
+int sd_abi_version(void) { return 2; }
 
 int sd_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
@@ -86,9 +102,14 @@ int sd_conv_fwd(const sd_conv_args* a, void* stream) {
   SD_REQUIRE(a != nullptr, "sd_conv_fwd: null args");
   SD_REQUIRE(a->taps == 1 || a->taps == 3, "sd_conv_fwd: taps must be 1 or 3 (got %d)", a->taps);
   SD_REQUIRE(a->Kp % 8 == 0 && a->Np % 8 == 0, "sd_conv_fwd: padded channel counts must be multiples of 8");
-  SD_REQUIRE(a->dtype == SD_F32 || a->dtype == SD_BF16, "sd_conv_fwd: bad dtype");
+  SD_REQUIRE(a->dtype == SD_F32 || a->dtype == SD_BF16 || a->dtype == SD_TF32, "sd_conv_fwd: bad dtype");
   SD_REQUIRE(a->B > 0 && a->T > 0, "sd_conv_fwd: empty input");
   const int impl = current_impl();
+  if (a->dtype == SD_TF32) {   // fp32 storage, TF32 / 3xTF32 tensor-core math: no CUDA-core stand-in
+    SD_REQUIRE(conv_fwd_tf32_supported(*a), "sd_conv_fwd: the TF32 tensor-core path does not support this configuration");
+    return conv_fwd_tf32(*a, (cudaStream_t)stream);
+  }
+  SD_REQUIRE(a->in_lo == nullptr && a->w_lo == nullptr, "sd_conv_fwd: operand low planes need dtype SD_TF32");
   SD_REQUIRE(a->affine == nullptr || (impl != SD_IMPL_SIMT && conv_fwd_tc_supported(*a)),
              "sd_conv_fwd: the fused per-channel affine (eval-mode BatchNorm) needs the tensor-core path with SD_ACT_GELU and a BTC output");
   if (impl == SD_IMPL_TC) {
@@ -96,6 +117,7 @@ int sd_conv_fwd(const sd_conv_args* a, void* stream) {
     return conv_fwd_tc(*a, (cudaStream_t)stream);
   }
   if (impl == SD_IMPL_AUTO && conv_fwd_tc_supported(*a)) return conv_fwd_tc(*a, (cudaStream_t)stream);
+  if (a->dtype == SD_BF16 && impl == SD_IMPL_AUTO) warn_simt_fallback("sd_conv_fwd", a->N, a->K, a->taps, a->act, a->out_mode);
   return conv_fwd_simt(*a, (cudaStream_t)stream);
 }
 
@@ -103,13 +125,19 @@ int sd_conv_wgrad(const sd_wgrad_args* a, void* stream) {
   SD_REQUIRE(a != nullptr, "sd_conv_wgrad: null args");
   SD_REQUIRE(a->taps == 1 || a->taps == 3, "sd_conv_wgrad: taps must be 1 or 3");
   SD_REQUIRE(a->Kp % 8 == 0 && a->Np % 8 == 0, "sd_conv_wgrad: padded channel counts must be multiples of 8");
-  SD_REQUIRE(a->dtype == SD_F32 || a->dtype == SD_BF16, "sd_conv_wgrad: bad dtype");
+  SD_REQUIRE(a->dtype == SD_F32 || a->dtype == SD_BF16 || a->dtype == SD_TF32, "sd_conv_wgrad: bad dtype");
   const int impl = current_impl();
+  if (a->dtype == SD_TF32) {
+    SD_REQUIRE(conv_wgrad_tf32_supported(*a), "sd_conv_wgrad: the TF32 tensor-core path does not support this configuration");
+    return conv_wgrad_tf32(*a, (cudaStream_t)stream);
+  }
+  SD_REQUIRE(a->dout_lo == nullptr && a->in_lo == nullptr, "sd_conv_wgrad: operand low planes need dtype SD_TF32");
   if (impl == SD_IMPL_TC) {
     SD_REQUIRE(conv_wgrad_tc_supported(*a), "sd_conv_wgrad: tcgen05 path does not support this configuration");
     return conv_wgrad_tc(*a, (cudaStream_t)stream);
   }
   if (impl == SD_IMPL_AUTO && conv_wgrad_tc_supported(*a)) return conv_wgrad_tc(*a, (cudaStream_t)stream);
+  if (a->dtype == SD_BF16 && impl == SD_IMPL_AUTO) warn_simt_fallback("sd_conv_wgrad", a->N, a->K, a->taps, 0, 0);
   return conv_wgrad_simt(*a, (cudaStream_t)stream);
 }
 

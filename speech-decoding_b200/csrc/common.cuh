@@ -178,5 +178,9 @@ int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st);
 bool conv_fwd_tc_supported(const sd_conv_args& a);
 void set_conv_pair(int on, bool ws);   // conv forward: allow 2-CTA (cta_group::2) tiles / weight-stationary pairs
 bool conv_wgrad_tc_supported(const sd_wgrad_args& a);
+int conv_fwd_tf32(const sd_conv_args& a, cudaStream_t st);      // conv_tf32.cu
+bool conv_fwd_tf32_supported(const sd_conv_args& a);
+int conv_wgrad_tf32(const sd_wgrad_args& a, cudaStream_t st);   // wgrad_tf32.cu
+bool conv_wgrad_tf32_supported(const sd_wgrad_args& a);
 
 }  // namespace sd

@@ -454,6 +454,13 @@ int pick_block_c(int kp) {
 
 }  // namespace
 
+// split-K reduce, shared with wgrad_tf32.cu
+int wgrad_reduce_launch(const float* ws, const float* ws_bias, float* dw, float* dbias, int N, int K, int taps, int wrows,
+                        int wcols, int nsplit, long long sn, long long sk, long long sj, cudaStream_t st) {
+  wgrad_reduce_kernel<<<dim3(cdiv(K, 128), N, taps), 128, 0, st>>>(ws, ws_bias, dw, dbias, N, K, taps, wrows, wcols, nsplit, sn, sk, sj);
+  return check_launch("wgrad_reduce");
+}
+
 bool conv_wgrad_tc_supported(const sd_wgrad_args& a) {
   if (a.dtype != SD_BF16) return false;
   if (((uintptr_t)a.dout & 15) || ((uintptr_t)a.in & 15)) return false;

@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsd_b200.so")
 
-SD_F32, SD_BF16 = 0, 1
+SD_F32, SD_BF16, SD_TF32 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_GLU = 0, 1, 2
 OUT_BTC, OUT_NCT_F32 = 0, 1
 SA_MPARTS = 32          # SD_SA_MPARTS
@@ -21,7 +21,7 @@ class ConvArgs(C.Structure):
                 ("preact", vp), ("stats", vp), ("rownorm2", vp),
                 ("B", i32), ("T", i32), ("K", i32), ("Kp", i32), ("N", i32), ("Np", i32),
                 ("taps", i32), ("dil", i32), ("G", i32),
-                ("act", i32), ("out_mode", i32), ("dtype", i32), ("affine", vp)]
+                ("act", i32), ("out_mode", i32), ("dtype", i32), ("affine", vp), ("in_lo", vp), ("w_lo", vp)]
 
 
 class AdamEntry(C.Structure):
@@ -35,7 +35,7 @@ class WgradArgs(C.Structure):
                 ("B", i32), ("T", i32), ("K", i32), ("Kp", i32), ("N", i32), ("Np", i32),
                 ("taps", i32), ("dil", i32), ("G", i32),
                 ("gs", i64), ("sn", i64), ("sk", i64), ("sj", i64), ("dtype", i32),
-                ("workspace", vp), ("workspace_bytes", i64)]
+                ("workspace", vp), ("workspace_bytes", i64), ("dout_lo", vp), ("in_lo", vp)]
 
 
 class PackEntry(C.Structure):
@@ -80,6 +80,7 @@ SIGNATURES = {
     "sd_clip_dots_tc_bf16": [vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_dz_tc_bf16": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_dz": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
+    "sd_tf32_split": [vp, vp, vp, i64, vp],
     "sd_peer_alloc": [C.POINTER(vp), i64],
     "sd_peer_free": [vp],
     "sd_ipc_handle_bytes": [],

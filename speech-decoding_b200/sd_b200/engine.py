@@ -43,16 +43,31 @@ class WeightPack:
         self.specs.append((name, list(params), N, K, taps))
 
     def refresh(self, device, dtype):
-        sig = (str(device), dtype) + tuple(p.data_ptr() for s in self.specs for p in s[1])
+        split = ops.tensor_core_fp32() == 3 and dtype == torch.float32
+        sig = (str(device), dtype, split) + tuple(p.data_ptr() for s in self.specs for p in s[1])
         if sig != self._sig:
             entries = []
             self.bufs = {}
             code = nat.SD_F32 if dtype == torch.float32 else nat.SD_BF16
-            for name, params, N, K, taps in self.specs:
+            # every shadow lives in ONE flat buffer (3xTF32: the packed weights are split into hi / lo planes by a
+            # single launch over it)
+            sizes = [(len(params) * taps * rup8(N) * rup8(K)) for _, params, N, K, taps in self.specs]
+            self._flat = torch.empty(2 * sum(sizes), dtype=dtype, device=device)
+            self._planes = torch.empty((2, 2 * sum(sizes)), dtype=dtype, device=device) if split else None
+            off = 0
+            for (name, params, N, K, taps), n in zip(self.specs, sizes):
                 G, Np, Kp = len(params), rup8(N), rup8(K)
-                wf = torch.empty((G, taps, Np, Kp), dtype=dtype, device=device)
-                wd = torch.empty((G, taps, Kp, Np), dtype=dtype, device=device)
-                self.bufs[name] = (wf, wd)
+                wf = self._flat[off:off + n].view(G, taps, Np, Kp)
+                wd = self._flat[off + n:off + 2 * n].view(G, taps, Kp, Np)
+                if split:
+                    hf = self._planes[0, off:off + n].view(G, taps, Np, Kp)
+                    hd = self._planes[0, off + n:off + 2 * n].view(G, taps, Kp, Np)
+                    hf._sd_lo = self._planes[1, off:off + n].view(G, taps, Np, Kp)
+                    hd._sd_lo = self._planes[1, off + n:off + 2 * n].view(G, taps, Kp, Np)
+                    self.bufs[name] = (hf, hd)
+                else:
+                    self.bufs[name] = (wf, wd)
+                off += 2 * n
                 for g, p in enumerate(params):
                     if p.dtype != torch.float32 or not p.is_contiguous():
                         raise RuntimeError("sd_b200: parameter %s must be contiguous fp32" % name)
@@ -65,6 +80,9 @@ class WeightPack:
             self._max_tiles = max(((e.Np + 31) // 32) * ((e.Kp + 31) // 32) for e in entries)
             self._sig = sig
         nat.call("sd_pack_weights", self._table.data_ptr(), self._n, self._max_tiles, ops._st())
+        if split:
+            nat.call("sd_tf32_split", self._flat.data_ptr(), self._planes[0].data_ptr(), self._planes[1].data_ptr(),
+                     self._flat.numel(), ops._st())
 
     def wf(self, name):
         return self.bufs[name][0]

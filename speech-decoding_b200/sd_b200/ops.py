@@ -7,13 +7,16 @@ import torch
 
 from . import _native as nat
 
-_PRECISIONS = {"fp32": (torch.float32, nat.SD_F32), "bf16": (torch.bfloat16, nat.SD_BF16)}
+_PRECISIONS = {"fp32": (torch.float32, nat.SD_F32), "bf16": (torch.bfloat16, nat.SD_BF16),
+               "tf32": (torch.float32, nat.SD_F32), "tf32x3": (torch.float32, nat.SD_F32)}
 _precision = os.environ.get("SD_B200_PRECISION", "bf16")
 
 
 def set_precision(p: str):
-    """'bf16' (default; bf16 activations/weight shadows, fp32 accumulate and
-    master parameters) or 'fp32' (fp32 everywhere; exact-parity mode)."""
+    """'bf16' (default; bf16 activations/weight shadows, fp32 accumulate and master parameters),
+    'tf32' (fp32 storage, every conv / GEMM on tcgen05 kind::tf32 -- what the reference gets from cuDNN on a GPU),
+    'tf32x3' (fp32 storage, every conv product as three TF32 MMAs on pre-split hi/lo operands: fp32-class accuracy
+    on the tensor cores, the mode that meets the 1e-4 parity bar) or 'fp32' (fp32 everywhere on the CUDA cores)."""
     global _precision
     if p not in _PRECISIONS:
         raise ValueError("precision must be one of %s" % list(_PRECISIONS))
@@ -78,6 +81,23 @@ def require_cuda(t, name):
                            "(got device=%s)" % (name, t.device))
 
 
+def tensor_core_fp32():
+    """fp32 storage with TF32 tensor-core convolutions?  -> 0 (no), 1 (TF32), 3 (3xTF32)"""
+    return {"tf32": 1, "tf32x3": 3}.get(_precision, 0)
+
+
+def tf32_split(x):
+    """x fp32 -> (hi, lo) planes of the 3xTF32 kernels; a tensor that already carries its low plane (packed weights:
+    engine.WeightPack splits them once per step) is passed through."""
+    lo = getattr(x, "_sd_lo", None)
+    if lo is not None:
+        return x, lo
+    x = x.contiguous()
+    out = torch.empty((2,) + tuple(x.shape), dtype=torch.float32, device=x.device)
+    nat.call("sd_tf32_split", _p(x), _p(out[0]), _p(out[1]), x.numel(), _st())
+    return out[0], out[1]
+
+
 def code_of(t):
     if t.dtype == torch.float32:
         return nat.SD_F32
@@ -107,8 +127,15 @@ def conv_fwd(inp, w, *, K, N, taps=1, dil=1, bias=None, res=None, widx=None, G=1
              stats=None, rownorm2=None, act=nat.ACT_NONE, out_mode=nat.OUT_BTC, affine=None):
     B, T, Kp = inp.shape
     Np = rup8(N)
+    code, in_lo, w_lo = code_of(inp), None, None
+    tc32 = tensor_core_fp32() if inp.dtype == torch.float32 else 0
+    if tc32:
+        code = nat.SD_TF32
+        if tc32 == 3:
+            inp, in_lo = tf32_split(inp)
+            w, w_lo = tf32_split(w)
     a = nat.ConvArgs(_p(inp), _p(w), _p(bias), _p(res), _p(widx), _p(out), _p(preact), _p(stats), _p(rownorm2),
-                     B, T, K, Kp, N, Np, taps, dil, G, act, out_mode, code_of(inp), _p(affine))
+                     B, T, K, Kp, N, Np, taps, dil, G, act, out_mode, code, _p(affine), _p(in_lo), _p(w_lo))
     nat.call("sd_conv_fwd", a, _st())
     return out
 
@@ -130,10 +157,17 @@ def conv_wgrad(dout, inp, dw, *, K, N, taps=1, dil=1, dbias=None, order=None, of
     Kp = inp.shape[2]
     if strides is None:                      # PyTorch Conv1d weight (N, K, taps)
         strides = (N * K * taps, K * taps, taps, 1)
-    ws = _wgrad_workspace(dout.device) if dout.dtype == torch.bfloat16 and G == 1 else None
+    code, dout_lo, in_lo = code_of(dout), None, None
+    tc32 = tensor_core_fp32() if dout.dtype == torch.float32 else 0
+    if tc32:
+        code = nat.SD_TF32
+        if tc32 == 3:
+            dout, dout_lo = tf32_split(dout)
+            inp, in_lo = tf32_split(inp)
+    ws = _wgrad_workspace(dout.device) if (dout.dtype == torch.bfloat16 or tc32) and G == 1 else None
     a = nat.WgradArgs(_p(dout), _p(inp), _p(dw), _p(dbias), _p(order), _p(offsets),
                       B, T, K, Kp, N, Np, taps, dil, G, strides[0], strides[1], strides[2], strides[3],
-                      code_of(dout), _p(ws), ws.numel() * 4 if ws is not None else 0)
+                      code, _p(ws), ws.numel() * 4 if ws is not None else 0, _p(dout_lo), _p(in_lo))
     nat.call("sd_conv_wgrad", a, _st())
 
 
@@ -210,7 +244,7 @@ def rownorm2(x2d):
 def clip_tc_ok(x2d, z2d):
     """tensor-core (TF32) CLIP kernels: used by the bf16 mode when the shape allows TMA"""
     M, D = x2d.shape
-    return (get_precision() == "bf16" and D % 4 == 0 and D >= 64
+    return (get_precision() in ("bf16", "tf32") and D % 4 == 0 and D >= 64
             and nat.lib().sd_clip_dots_workspace_bytes(M, z2d.shape[0], D) > 0)
 
 

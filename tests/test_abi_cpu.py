@@ -34,14 +34,31 @@ def test_ctypes_binding_covers_header():
 
 def test_abi_version_and_error_string():
     lib = _native.lib()
-    assert lib.sd_abi_version() == 1
+    assert lib.sd_abi_version() == 2
     assert isinstance(lib.sd_last_error(), bytes)
     assert lib.sd_set_impl(99) != 0
     assert b"sd_set_impl" in lib.sd_last_error()
 
 
-def test_struct_layout_matches_c():
-    # sizeof() as the C compiler lays the structs out (9 pointers + 12 ints; 6 pointers + 9 ints + 4 i64 + int)
-    assert ctypes.sizeof(_native.ConvArgs) == 9 * 8 + 12 * 4 + 8      # + the trailing `affine` pointer
-    assert ctypes.sizeof(_native.WgradArgs) == 6 * 8 + 9 * 4 + 4 + 4 * 8 + 8 + 16
-    assert ctypes.sizeof(_native.PackEntry) == 3 * 8 + 6 * 4
+def test_struct_layout_matches_c(tmp_path):
+    """sizeof / offsetof of every struct that crosses the boundary, as gcc lays them out from include/sd_b200.h,
+    against the ctypes mirrors in sd_b200/_native.py."""
+    import subprocess
+    structs = {"sd_conv_args": _native.ConvArgs, "sd_wgrad_args": _native.WgradArgs, "sd_pack_entry": _native.PackEntry,
+               "sd_adam_entry": _native.AdamEntry}
+    cname = {"inp": "in"}
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "sd_b200.h"', "int main(void) {"]
+    for cn, st in structs.items():
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (cn, cn))
+        for f, _ in st._fields_:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cn, f, cn, cname.get(f, f)))
+    src.append("return 0; }")
+    c = tmp_path / "abi.c"
+    c.write_text("\n".join(src))
+    exe = str(tmp_path / "abi")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", exe])
+    got = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+    for cn, st in structs.items():
+        assert int(got[cn]) == ctypes.sizeof(st), cn
+        for f, _ in st._fields_:
+            assert int(got["%s.%s" % (cn, f)]) == getattr(st, f).offset, (cn, f)

@@ -31,11 +31,14 @@ def build(cfg, precision):
     return args, BrainEncoder(args).to(DEV), CLIPLoss(args).to(DEV)
 
 
+STRICT = ("fp32", "tf32x3")      # precisions held to the fp32 bar with the max-norm metric
+
+
 def err_fn(precision):
     """fp32 mode: max-abs error over max-abs value (strict).  bf16 mode: normwise relative error
     ||a-b||/||b|| -- every stored activation is rounded to 8 mantissa bits, so individual elements of a
     17-layer network carry a few 1e-2 of noise while the tensors as a whole agree to <2e-2."""
-    return G.rel_err if precision == "fp32" else G.rel_l2
+    return G.rel_err if precision in STRICT else G.rel_l2
 
 
 def autocast_noise(sd, X, Y, ids, temp, mask, reduction="mean"):
@@ -192,7 +195,7 @@ def run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad, center=3, oracl
                              crit.temp.detach().to(od), mask.to(od))
     E = err_fn(precision)
     noise = None
-    if precision != "fp32":
+    if precision == "bf16":
         noise = autocast_noise(sd, X, Y, ids.tolist(), crit.temp.detach().cpu(), mask)
         PL.record("Z(autocast_bf16_floor)", noise["Z"], tol_out)
         tol_out = max(tol_out, 1.25 * noise["Z"])
@@ -214,19 +217,24 @@ def run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad, center=3, oracl
     clear = (gaps.min(dim=1)[0] > 1e-5) if gaps is not None else torch.ones(len(mine), dtype=torch.bool, device=mine.device)
     same = float((mine[clear] == ref_idx[clear]).all(dim=1).float().mean()) if int(clear.sum()) else 1.0
     PL.record("top10_rows_identical_frac", same, 1.0, rows_without_ties=int(clear.sum()))
-    if precision == "fp32":
+    if precision in STRICT:
         assert same == 1.0
     return worst
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 4e-2)])
+# tf32 (one TF32 MMA per product -- the arithmetic cuDNN gives the reference's convolutions on a GPU) is 10-bit
+# mantissa arithmetic: bounded normwise at 5e-3 / 2e-2; tf32x3 is held to the fp32 bar.
+PRECISIONS = [("fp32", 1e-4, 1e-4), ("tf32x3", 1e-4, 1e-4), ("tf32", 5e-3, 2e-2), ("bf16", 2e-2, 4e-2)]
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_grad", PRECISIONS)
 def test_cfg1_brennan_shape_vs_oracle(precision, tol_out, tol_grad):
     """BASELINE.json configs[0]: Brennan2018-shape EEG (60 ch, 3 s, B=64), full-width model."""
     args, X, Y, ids = oracle_case(B=64, C=60, T=360, S=33, D1=270, D2=320, Fo=1024, K=32, seed=1)
     run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad)
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 4e-2)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", PRECISIONS)
 def test_cfg5_long_window_vs_oracle(precision, tol_out, tol_grad):
     """BASELINE.json configs[4] shape class: T = 1200 (10 s x 120 Hz; 10 row tiles per sample with a ragged last
     tile, D = F*T = 153,600 for the CLIP GEMMs), reduced width so the oracle finishes in seconds."""
@@ -250,7 +258,7 @@ def test_cfg4_degenerate_subject_patterns(kind):
     run_vs_oracle(args, X, Y, ids, "fp32", 1e-4, 1e-4)
 
 
-@pytest.mark.parametrize("precision,tol_out,tol_grad", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 4e-2)])
+@pytest.mark.parametrize("precision,tol_out,tol_grad", PRECISIONS)
 def test_cfg2_full_size_vs_oracle(precision, tol_out, tol_grad):
     """BASELINE.json configs[1] AS BENCHMARKED: B=256, 208 sensors x 360 samples, 27 subjects, D1=270, D2=320, F=1024.
     Z, loss, every parameter gradient, the temperature gradient and the top-10 retrieval rows against the oracle run on
