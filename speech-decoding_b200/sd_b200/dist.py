@@ -68,6 +68,7 @@ class PeerGather:
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.NSTREAMS)]
         self.events = [torch.cuda.Event() for _ in range(self.NSTREAMS)]
         self.ready = torch.cuda.Event()
+        self.timing = None           # tools/dist_phases.py: list of (start, end) timing events of the pushes, per call
 
     def _release(self):
         from . import _native as nat
@@ -122,15 +123,23 @@ class PeerGather:
         nbytes = rows * D * 2
         off = slot * self.slot_bytes + self.rank * nbytes
         self.ready.record()
+        t_ev = None
+        if self.timing is not None:
+            t_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         for k in range(self.world):               # k = 0 is the local slot; peers in ring order so that no two ranks
             peer = (self.rank + k) % self.world   # push into the same destination at the same time
             st = self.streams[k % self.NSTREAMS]
             if k < self.NSTREAMS:
                 st.wait_event(self.ready)
+                if k == 0 and t_ev is not None:
+                    t_ev[0].record(st)
             nat.call("sd_memcpy_async", self.peers[peer] + off, xb.data_ptr(), nbytes, st.cuda_stream)
         for i in range(1, min(self.NSTREAMS, self.world)):
             self.events[i].record(self.streams[i])
             self.streams[0].wait_event(self.events[i])
+        if t_ev is not None:
+            t_ev[1].record(self.streams[0])
+            self.timing.append(t_ev)
         norms = torch.empty((self.world * rows,), dtype=n2.dtype, device=n2.device)
         with torch.cuda.stream(self.streams[0]):
             work = dist.all_gather_into_tensor(norms, n2, group=self.group, async_op=True)

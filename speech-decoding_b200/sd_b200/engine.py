@@ -22,7 +22,6 @@ from . import ops
 from .ops import rup8
 
 FUSE_EVAL_BN = True     # inference: fold eval-mode BatchNorm + GELU into the producing conv epilogue (tests flip it)
-BN_MOMENTUM, BN_EPS = 0.1, 1e-5          # nn.BatchNorm1d defaults (models.py:135,143)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -279,14 +278,28 @@ class ConvBlockStage(Stage):
         pack.add(self.key + ".c1", [m.conv1.weight], m.D2, m.D2, 3)
         pack.add(self.key + ".c2", [m.conv2.weight], 2 * m.D2, m.D2, 3)
 
+    @staticmethod
+    def _bn_config(bn):
+        """momentum / eps / mode of ONE BatchNorm1d module (models.py:135,143 use the defaults, but a loaded or edited
+        module is honoured); configurations the kernels do not implement raise instead of being silently ignored."""
+        if bn.momentum is None:
+            raise NotImplementedError("sd_b200: BatchNorm1d(momentum=None) (cumulative moving average) is not supported")
+        if not bn.track_running_stats or bn.running_mean is None or bn.running_var is None:
+            raise NotImplementedError("sd_b200: BatchNorm1d(track_running_stats=False) is not supported")
+        if not bn.affine:
+            raise NotImplementedError("sd_b200: BatchNorm1d(affine=False) is not supported")
+        return float(bn.momentum), float(bn.eps), bool(bn.training)
+
     def _bn(self, run, bn, stats, n, ss):
-        training = bn.training or bn.running_mean is None
+        momentum, eps, training = self._bn_config(bn)
+        if training and stats is None:
+            raise RuntimeError("sd_b200: training-mode BatchNorm needs the batch statistics of its producing conv")
         if training and run.bn_group is not None:
             import torch.distributed as dist
             dist.all_reduce(stats, group=run.bn_group)
             n = n * dist.get_world_size(run.bn_group)
         ops.bn_finalize(stats, bn.num_features, rup8(bn.num_features), n, bn.weight, bn.bias, bn.running_mean,
-                        bn.running_var, bn.num_batches_tracked, BN_MOMENTUM, BN_EPS, training, ss)
+                        bn.running_var, bn.num_batches_tracked, momentum, eps, training, ss)
         return training
 
     def forward(self, run, x, sv):
@@ -297,6 +310,8 @@ class ConvBlockStage(Stage):
         d0, d1 = m.conv0.dilation[0], m.conv1.dilation[0]
         dev, dt = x.device, run.dtype
         train = m.batchnorm0.training
+        if m.batchnorm1.training != train:
+            raise NotImplementedError("sd_b200: the two BatchNorm layers of a ConvBlock must be in the same mode")
         stats = run.scratch.take(4 * D2p).view(2, 2 * D2p) if train else None
         ss = torch.empty((2, 4 * D2p), dtype=torch.float32, device=dev)
         if (not train and sv is None and dt == torch.bfloat16 and FUSE_EVAL_BN and D2 % 8 == 0

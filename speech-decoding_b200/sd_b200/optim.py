@@ -26,6 +26,12 @@ class FusedAdam(torch.optim.Optimizer):
         self._ring = []            # [host pinned uint8, device uint8, event]
         self._turn = 0
 
+    def __getstate__(self):
+        # pinned staging buffers and CUDA events are per-process scratch: never pickled / deep-copied
+        d = self.__dict__.copy()
+        d["_ring"], d["_turn"] = [], 0
+        return d
+
     @staticmethod
     def _real(t):
         return torch.view_as_real(t) if t.is_complex() else t
@@ -36,15 +42,23 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        # validate every parameter BEFORE touching any state: a step that raises must not leave step counts advanced
         for group in self.param_groups:
-            beta1, beta2 = group["betas"]
-            entries, device, max_n = [], None, 0
             for p in group["params"]:
                 if p.grad is None:
                     continue
                 ops.require_cuda(p, "parameter")
                 if p.dtype not in (torch.float32, torch.complex64) or p.grad.is_sparse:
                     raise TypeError("FusedAdam supports dense float32 / complex64 parameters")
+                if not p.is_contiguous():
+                    raise ValueError("FusedAdam needs contiguous parameters")
+        ring_size = max(4, len(self.param_groups))       # one staging buffer per group and step in flight
+        for group in self.param_groups:
+            beta1, beta2 = group["betas"]
+            entries, device, max_n = [], None, 0
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
                 st = self.state[p]
                 if not st:
                     st["step"] = torch.tensor(0.0, dtype=torch.float32)
@@ -52,8 +66,6 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
                 step = float(st["step"])
-                if not p.is_contiguous():
-                    raise ValueError("FusedAdam needs contiguous parameters")
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 pr, gr, m, v = self._real(p), self._real(g), self._real(st["exp_avg"]), self._real(st["exp_avg_sq"])
                 n = pr.numel()
@@ -65,7 +77,7 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             k = len(entries)
             nbytes = k * ctypes.sizeof(nat.AdamEntry)
-            if len(self._ring) < 4:
+            if len(self._ring) < ring_size:
                 self._ring.append(None)
             self._turn = (self._turn + 1) % len(self._ring)
             slot = self._ring[self._turn]

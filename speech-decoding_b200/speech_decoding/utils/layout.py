@@ -2,14 +2,18 @@
 speech_decoding/utils/layout.py:6-43).
 
 The reference reads real montages through `mne` / `mne_bids` and the dataset on
-disk.  When those are importable this module does the same; otherwise -- and
-whenever `args` carries an explicit layout -- it returns a synthetic layout that
-honours the same post-conditions (float32 (C,2), per-axis min-max normalised,
+disk, and fails hard when either is missing.  So does this module -- unless the
+caller EXPLICITLY opts into a stand-in layout (tests, benchmarks, synthetic data),
+which honours the same post-conditions (float32 (C,2), per-axis min-max normalised,
 scaled to [0.1, 0.9]; layout.py:37-43):
 
-  args.sensor_layout : optional (C,2) array/tensor of raw 2-D positions
-  args.num_channels  : sensor count for the seeded synthetic layout
-  args.layout_seed   : seed of the synthetic layout (default 0)
+  args.sensor_layout    : (C,2) array/tensor of raw 2-D positions, used as given, or
+  args.layout_seed      : seed of a synthetic uniform layout (its presence is the opt-in;
+  args.synthetic_layout : ... as is this flag), with args.num_channels sensors
+
+A missing `mne` install or an unreadable dataset is never papered over with fake geometry:
+SpatialAttention's Fourier tables and SpatialDropout's distances would silently be wrong
+(and SpatialDropout.loc is not in the state_dict, so not even a checkpoint would repair it).
 """
 import numpy as np
 import torch
@@ -45,23 +49,22 @@ def ch_locations_2d(args):
             explicit = explicit.detach().cpu().numpy()
         return _normalise(explicit)
     dataset = _get(args, "dataset")
+    seed = _get(args, "layout_seed")
+    if seed is not None or _get(args, "synthetic_layout"):          # explicit opt-in to a stand-in layout
+        n = _get(args, "num_channels")
+        if n is None:
+            n = {"Brennan2018": 60, "Gwilliams2022": 208}.get(dataset)
+        if n is None:
+            raise ValueError("synthetic sensor layout requested but neither num_channels nor a known dataset given (%r)" % (dataset,))
+        return synthetic_layout(n, seed or 0)
     try:
         import mne                                     # noqa: F401
-        have_mne = hasattr(mne, "channels")
-    except Exception:
-        have_mne = False
-    if have_mne:
-        try:
-            return _from_mne(dataset, _get(args, "root_dir"))
-        except Exception:
-            if _get(args, "num_channels") is None:
-                raise
-    n = _get(args, "num_channels")
-    if n is None:
-        n = {"Brennan2018": 60, "Gwilliams2022": 208}.get(dataset)
-    if n is None:
-        raise ValueError("unknown dataset %r and no num_channels / sensor_layout given" % (dataset,))
-    return synthetic_layout(n, _get(args, "layout_seed", 0) or 0)
+    except ImportError as e:
+        raise ImportError("speech_decoding.utils.layout: the sensor layout of %r needs `mne` (and `mne_bids` + the dataset "
+                          "under args.root_dir for Gwilliams2022), exactly like the reference (layout.py:1-32).  For "
+                          "synthetic data pass args.sensor_layout, or args.layout_seed / args.synthetic_layout with "
+                          "args.num_channels." % (dataset,)) from e
+    return _from_mne(dataset, _get(args, "root_dir"))
 
 
 def _from_mne(dataset, root_dir):
@@ -79,5 +82,5 @@ def _from_mne(dataset, root_dir):
         raw = mne_bids.read_raw_bids(path)
         pos = mne.channels.find_layout(raw.info, ch_type="meg").pos[:, :2]
     else:
-        raise ValueError()
+        raise ValueError("unknown dataset %r (layout.py:34)" % (dataset,))
     return _normalise(pos)

@@ -104,3 +104,25 @@ def test_next_row_helpers_refuse_cpu_and_keep_the_reference_contracts():
         FusedAdam([p], amsgrad=True)
     with pytest.raises(ValueError):
         FusedAdam([p], lr=-1.0)
+
+
+def test_sensor_layout_is_never_faked_silently(monkeypatch):
+    """Without an explicit opt-in (sensor_layout / layout_seed / synthetic_layout) a missing `mne` install or dataset is a
+    hard error, as in the reference (layout.py:1-32) -- no silent random geometry."""
+    import pytest
+    from types import SimpleNamespace
+    from speech_decoding.utils.layout import ch_locations_2d
+    import sys
+    if "mne" in sys.modules and getattr(sys.modules["mne"], "__file__", None) is None:
+        monkeypatch.delitem(sys.modules, "mne")        # the empty stand-in module oracle/ref_import.py installs
+    try:
+        import mne  # noqa: F401
+        pytest.skip("mne is installed here: the error path under test needs it absent")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError):
+        ch_locations_2d(SimpleNamespace(dataset="Gwilliams2022", root_dir="/nonexistent", num_channels=208))
+    loc = ch_locations_2d(SimpleNamespace(dataset="Gwilliams2022", root_dir="/nonexistent", num_channels=208, layout_seed=0))
+    assert loc.shape == (208, 2) and float(loc.min()) == pytest.approx(0.1) and float(loc.max()) == pytest.approx(0.9)
+    loc = ch_locations_2d(SimpleNamespace(dataset="x", sensor_layout=np.random.rand(5, 2)))
+    assert loc.shape == (5, 2)
