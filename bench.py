@@ -37,8 +37,9 @@ ENC_FWD_GF, ENC_BWD_GF = 5.154, 10.267
 
 
 def step_gflop_per_sample(global_b):
+    scale = CFG["T"] / 360.0                      # every encoder FLOP is per time step (T = 360 in SURVEY 8d)
     clip = 2.0 * global_b * CFG["F"] * CFG["T"] / 1e9
-    return ENC_FWD_GF + ENC_BWD_GF + 2 * clip
+    return (ENC_FWD_GF + ENC_BWD_GF) * scale + 2 * clip
 
 
 def measured_peaks():
@@ -294,13 +295,20 @@ def run_ours(a, rank, world, local_rank):
     args = make_args_ns()
     enc = BrainEncoder(args).to(dev).train()
     crit = CLIPLoss(args).to(dev).train()
-    opt = torch.optim.Adam(list(enc.parameters()) + list(crit.parameters()), lr=3e-4)
+    from sd_b200.optim import FusedAdam
+    opt = FusedAdam(list(enc.parameters()) + list(crit.parameters()), lr=3e-4)     # train.py:161-163, one launch per step
     dp = None
     if world > 1:
         from sd_b200.dist import DataParallel
         dp = DataParallel(enc, crit, sync_bn=bool(a.sync_bn))
     B = a.batch
-    Xh, Yh, ids = synth(B, 1000 + rank, pin=True)
+    Xh, Yh, ids = synth(B, 1000 + rank, pin=False)
+    # speech embeddings: a frozen wav2vec2 output, i.e. dataset content.  In the bf16 mode they are held (host and device)
+    # in bf16 -- rounded ONCE when the dataset is built; the bf16 CLIP GEMMs round them anyway -- unless --speech-dtype fp32
+    y_bf16 = a.precision == "bf16" and a.speech_dtype == "bf16"
+    if y_bf16:
+        Yh = Yh.to(torch.bfloat16)
+    Xh, Yh = Xh.pin_memory(), Yh.pin_memory()
     X, Y = Xh.to(dev), Yh.to(dev)
 
     def barrier():
@@ -446,20 +454,23 @@ def run_ours(a, rank, world, local_rank):
     line = {"metric": "BrainEncoder+CLIP train samples/sec", "value": round(value, 1), "unit": "samples/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-            "config": {"workload": "cfg2/cfg3 Gwilliams2022-shape MEG: B=%d per GPU, 208 sensors x 360 samples, 27 subjects, "
+            "config": {"workload": "%s Gwilliams2022-shape MEG: B=%d per GPU, 208 sensors x %d samples, 27 subjects, "
                                    "D1=270 D2=320 F=1024 K=32; step = encoder fwd + CLIP loss + backward%s"
-                                   % (B, " + grad all-reduce, global-batch CLIP negatives" if world > 1 else ""),
+                                   % ("cfg2/cfg3" if CFG["T"] == 360 else "cfg5 long-window" if CFG["T"] == 1200 else "custom-window",
+                                      B, CFG["T"], " + grad all-reduce, global-batch CLIP negatives" if world > 1 else ""),
+                       "speech_embeddings": "bf16 (rounded once on the host)" if y_bf16 else "fp32",
                        "global_batch": world * B,
                        "precision": a.precision + {"bf16": " activations, fp32 master weights/accumulate",
                                                    "tf32": ": fp32 storage, tcgen05 kind::tf32 convolutions / GEMMs (the reference's cuDNN default)",
                                                    "tf32x3": ": fp32 storage, 3xTF32 split convolutions on tcgen05 (fp32-class accuracy), fp32 CLIP",
                                                    "fp32": ": fp32 CUDA-core kernels"}[a.precision],
-                       "l2": "working set (>2 GB of activations, 454 MB of inputs) exceeds the 126 MB L2",
+                       "l2": "working set (>2 GB of activations, >260 MB of inputs) exceeds the 126 MB L2: no flush needed between steps",
                        "sync_bn": bool(a.sync_bn) if world > 1 else None, "loss": round(loss_val, 4)},
             "model_tflops_per_s": round(value * gflop / 1e3, 1),
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 3),
-                    "h2d_bytes_per_step": int(Xh.numel() * 4 + Yh.numel() * 4), "d2h_bytes_per_step": 4,
-                    "includes": "H2D of X,Y from pinned memory (double-buffered), fwd, loss, backward, Adam step, loss.item()"},
+                    "h2d_bytes_per_step": int(Xh.numel() * Xh.element_size() + Yh.numel() * Yh.element_size()), "d2h_bytes_per_step": 4,
+                    "includes": "H2D of X (fp32) and Y (%s) from pinned memory (double-buffered on a copy stream), fwd, loss, backward, "
+                                "fused Adam step (sd_adam_step), loss.item()" % ("bf16" if y_bf16 else "fp32")},
             "gpu_launches": launches, "clocks": clk}
     if dp is not None:
         red = enc.pipeline().reducer
@@ -485,8 +496,13 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3", "fp32"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--sync-bn", type=int, default=0)
+    ap.add_argument("--speech-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="storage of the (frozen) speech embeddings Y in the bf16 mode")
+    ap.add_argument("--window", type=int, default=CFG["T"],
+                    help="samples per window: 360 = 3 s (cfg2/cfg3), 1200 = 10 s (BASELINE.json configs[4])")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    CFG["T"] = a.window
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -228,6 +228,8 @@ int sd_clip_dz_tc(const float* coef_t, const float* cz, const float* x, const fl
  *   sd_clip_dots_tc_bf16 / sd_clip_dz_tc_bf16: as the tf32 forms with x, z (dots) and coef_t, x (dz) in bf16;
  *   the projection row z and dz stay fp32. */
 int sd_cast_rows_bf16(const float* x, void* y, float* nrm2, int M, int64_t D, void* stream);
+/* squared norms of rows that already are bf16 (M, D), D % 8 == 0: speech embeddings shipped from the host in bf16 */
+int sd_rownorm2_bf16(const void* x, float* nrm2, int M, int64_t D, void* stream);
 int sd_clip_coef_t_bf16(const float* coef, void* coef_t, int M, int N, int Mp, void* stream);
 int sd_clip_dots_tc_bf16(const void* x, const void* z, float* dots, void* workspace, int M, int N, int64_t D,
                          void* stream);

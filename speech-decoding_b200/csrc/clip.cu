@@ -80,6 +80,34 @@ __global__ void __launch_bounds__(256) cast_rows_bf16_kernel(const float* __rest
   }
 }
 
+// squared norms of rows that are ALREADY bf16 (speech embeddings shipped from the host in bf16: they are a frozen wav2vec2
+// output, rounded once when the dataset is built, so the step never touches an fp32 copy of them)
+__global__ void __launch_bounds__(256) rownorm2_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t D,
+                                                            int64_t chunk) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  const int64_t d0 = (int64_t)blockIdx.y * chunk, d1 = min(D, d0 + chunk);
+  const __nv_bfloat16* row = x + (size_t)i * D;
+  float s = 0.f;
+  for (int64_t d = d0 + threadIdx.x * 8; d < d1; d += 2048) {     // D % 8 == 0 on this path
+    const uint4 q = *reinterpret_cast<const uint4*>(row + d);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+      s = fmaf(f.x, f.x, fmaf(f.y, f.y, s));
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out + i, t);
+  }
+}
+
 // coefT[j, i] (bf16, row stride Mp) = coef[i, j]: A operand of the bf16 gradient GEMM
 __global__ void coef_t_bf16_kernel(const float* __restrict__ coef, __nv_bfloat16* __restrict__ ct, int M, int N, int Mp) {
   __shared__ float tile[32][33];
@@ -341,6 +369,18 @@ int sd_cast_rows_bf16(const float* x, void* y, float* nrm2, int M, int64_t D, vo
   splits = cdiv(D, chunk);
   cast_rows_bf16_kernel<<<dim3(M, splits), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), nrm2, D, chunk);
   return check_launch("cast_rows_bf16");
+}
+
+int sd_rownorm2_bf16(const void* x, float* nrm2, int M, int64_t D, void* stream) {
+  SD_REQUIRE(D % 8 == 0 && (((uintptr_t)x) & 15) == 0, "sd_rownorm2_bf16: D %% 8 != 0 or unaligned rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  SD_CUDA(cudaMemsetAsync(nrm2, 0, sizeof(float) * M, st));
+  int splits = cdiv(148 * 8, M);
+  int64_t chunk = (D + splits - 1) / splits;
+  chunk = (chunk + 2047) / 2048 * 2048;
+  splits = cdiv(D, chunk);
+  rownorm2_bf16_kernel<<<dim3(M, splits), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), nrm2, D, chunk);
+  return check_launch("rownorm2_bf16");
 }
 
 int sd_clip_coef_t_bf16(const float* coef, void* coef_t, int M, int N, int Mp, void* stream) {

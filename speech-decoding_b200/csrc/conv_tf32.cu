@@ -9,8 +9,13 @@
 //   * TF32      (in_lo == w_lo == NULL): one kind::tf32 MMA per product -- 10-bit mantissas, ~1e-3.
 //   * 3xTF32    (in_lo, w_lo given): every operand arrives pre-split as x = hi + lo with hi = x rounded to TF32
 //               (low 13 mantissa bits zero) and lo = the TF32 rounding of x - hi (sd_tf32_split), and the
-//               kernel accumulates  hi*hi + hi*lo + lo*hi  into the same fp32 TMEM accumulator: three MMAs per
-//               product, error ~2^-21 -- the mode that meets the 1e-4 parity bar ON the tensor cores.
+//               kernel accumulates  hi*hi + hi*lo + lo*hi: three MMAs per product, operand error ~2^-21 -- the mode
+//               that meets the 1e-4 parity bar ON the tensor cores.  The tensor core adds into its fp32 accumulator
+//               with truncation (a bias of up to one ulp per MMA, all in the same direction), which over a 360-MMA
+//               chain is what limits a plain 3xTF32 kernel to ~2e-5 per op; so the hi*hi products of even and odd
+//               k-blocks go to two separate TMEM accumulators and the two small cross terms to a third, and the
+//               epilogue adds the three in round-to-nearest fp32: chains six times shorter, small terms out of
+//               the big sum.  (Three accumulators of <= 160 columns: no double buffering in this variant.)
 //
 // GEMM view per CTA tile:  D[128 time rows, BLOCK_N channels] = sum_{pass} sum_{tap j} sum_{k-block}
 //     A_j[128 x 32] (fp32 activations, channels-last => K-major, rows t0+shift_j.., zero-filled outside [0,T))
@@ -50,6 +55,7 @@ struct Tf32Params {
   int block_n, n_tiles, m_tiles_per_sample, num_tiles, k_blocks;
   int act, out_mode, D2, Op;
   int planes;      // 1: TF32, 2: operands split hi/lo (3xTF32)
+  int acc_stride;  // 3xTF32: TMEM columns between the three partial accumulators
   int sa_slots, sw_slots, a_bytes, w_bytes, a_rows, halo, off_w, off_bias, off_stats, off_bar, cols_alloc;
 };
 
@@ -202,31 +208,37 @@ conv_fwd_tf32_kernel(const __grid_constant__ Tf32Maps tm, const Tf32Params p) {
     int sa = 0, sw = 0;
     uint32_t pha = 0, phw = 0;
     int it_tile = 0;
+    const bool x3 = p.planes == 2;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it_tile) {
-      const int acc = it_tile & 1;
-      const uint32_t acc_ph = (it_tile >> 1) & 1;
+      // TF32: two accumulator buffers of 256 columns, alternating per tile.  3xTF32: ONE buffer of three accumulators
+      // (hi*hi of even k-blocks | hi*hi of odd k-blocks | cross terms), p.acc_stride columns apart.
+      const int acc = x3 ? 0 : (it_tile & 1);
+      const uint32_t acc_ph = x3 ? (it_tile & 1) : ((it_tile >> 1) & 1);
       mbar_wait(tempty_bar(acc), acc_ph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * MAX_BLOCK_N;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(afull_bar(sa), pha);
         const uint32_t alo = smem_desc_lo(smem_base + sa * (p.planes * p.a_bytes), 16);
+        const uint32_t d_main = x3 ? d_tmem + (kb & 1) * p.acc_stride : d_tmem;
+        const uint32_t d_small = d_tmem + 2 * p.acc_stride;
         for (int j = 0; j < TAPS; ++j) {
           mbar_wait(wfull_bar(sw), phw);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t blo = smem_desc_lo(smem_base + p.off_w + sw * (p.planes * p.w_bytes), 16);
             const uint32_t aj = alo + j * tap_step;
+            const uint32_t first_main = x3 ? (uint32_t)(kb < 2 && j == 0) : (uint32_t)((kb | j) == 0);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 8; ++k)   // +32 B per 8-element k-step inside the swizzled row
-              umma_tf32(d_tmem, desc64(aj + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, (kb | j | k) != 0);
-            if (p.planes == 2) {
+              umma_tf32(d_main, desc64(aj + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, !(first_main && k == 0));
+            if (x3) {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / 8; ++k)   // hi * lo
-                umma_tf32(d_tmem, desc64(aj + 2 * k, dhi), desc64(blo + w_plane + 2 * k, dhi), idesc, 1);
+                umma_tf32(d_small, desc64(aj + 2 * k, dhi), desc64(blo + w_plane + 2 * k, dhi), idesc, (kb | j | k) != 0);
 #pragma unroll
               for (int k = 0; k < BLOCK_K / 8; ++k)   // lo * hi
-                umma_tf32(d_tmem, desc64(aj + a_plane + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, 1);
+                umma_tf32(d_small, desc64(aj + a_plane + 2 * k, dhi), desc64(blo + 2 * k, dhi), idesc, 1);
             }
             umma_commit(wempty_bar(sw));
             if (j == TAPS - 1) {
@@ -251,9 +263,32 @@ conv_fwd_tf32_kernel(const __grid_constant__ Tf32Maps tm, const Tf32Params p) {
     const int ch0 = hsel ? (nch + 1) / 2 : 0;
     const int ch1 = hsel ? nch : (nch + 1) / 2;
     int it_tile = 0;
+    const bool x3 = p.planes == 2;
+    const bool two_main = x3 && p.k_blocks > 1;     // the odd-k-block accumulator exists
+    // 16 accumulator columns; 3xTF32: the sum of the three partial accumulators (round-to-nearest fp32 adds)
+    auto load_acc = [&](uint32_t addr, float (&v)[16]) {
+      uint32_t r[16];
+      tmem_ld16(addr, r);
+      if (x3) {
+        uint32_t r1[16], r2[16];
+        tmem_ld16(addr + 2 * p.acc_stride, r2);
+        if (two_main) tmem_ld16(addr + p.acc_stride, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float m = __uint_as_float(r[i]);
+          if (two_main) m += __uint_as_float(r1[i]);
+          v[i] = m + __uint_as_float(r2[i]);
+        }
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+      }
+    };
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it_tile) {
-      const int acc = it_tile & 1;
-      const uint32_t acc_ph = (it_tile >> 1) & 1;
+      const int acc = x3 ? 0 : (it_tile & 1);
+      const uint32_t acc_ph = x3 ? (it_tile & 1) : ((it_tile >> 1) & 1);
       const int m_idx = tile / p.n_tiles, n_idx = tile % p.n_tiles;
       const int b = m_idx / p.m_tiles_per_sample;
       const int t = (m_idx % p.m_tiles_per_sample) * BLOCK_M + quad * 32 + lane;
@@ -268,13 +303,9 @@ conv_fwd_tf32_kernel(const __grid_constant__ Tf32Maps tm, const Tf32Params p) {
       if (!glu) {
         for (int c = ch0; c < ch1; ++c) {
           const int cc = c * 16, nb = n0 + cc;
-          uint32_t r[16];
-          tmem_ld16(taddr + cc, r);
-          tmem_ld_wait();
-          if (nb >= p.Np) continue;     // (warp-uniform) chunk entirely beyond the tensor
           float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          load_acc(taddr + cc, v);
+          if (nb >= p.Np) continue;     // (warp-uniform) chunk entirely beyond the tensor
           lds16_add(s_bias + nb * 4, v);
           if (p.res && valid) {
             const float* rs = p.res + row * p.Np + nb;
@@ -330,14 +361,10 @@ conv_fwd_tf32_kernel(const __grid_constant__ Tf32Maps tm, const Tf32Params p) {
       } else {
         for (int c = ch0; c < ch1; ++c) {
           const int cc = c * 16, cb = n0 + cc;
-          uint32_t ra[16], rb[16];
-          tmem_ld16(taddr + cc, ra);
-          tmem_ld16(taddr + half_n + cc, rb);
-          tmem_ld_wait();
-          if (cb >= p.D2) continue;
           float va[16], vb[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(ra[i]); vb[i] = __uint_as_float(rb[i]); }
+          load_acc(taddr + cc, va);
+          load_acc(taddr + half_n + cc, vb);
+          if (cb >= p.D2) continue;
           lds16_add(s_bias + cb * 4, va);
           lds16_add(s_bias + (p.cols_alloc + cb) * 4, vb);
           if (valid) {
@@ -459,7 +486,8 @@ int conv_fwd_tf32(const sd_conv_args& a, cudaStream_t st) {
   const int n_total = glu ? 2 * p.Op : a.Np, gran = glu ? 32 : 16;
   int smem_bytes = 0;
   bool ok = false;
-  for (int max_bn = MAX_BLOCK_N; max_bn >= 64 && !ok; max_bn -= 32) {
+  // 3xTF32 keeps three accumulators of block_n columns in the 512 TMEM columns
+  for (int max_bn = (p.planes == 2 ? 160 : MAX_BLOCK_N); max_bn >= 64 && !ok; max_bn -= 32) {
     const int bn = pick_block_n_tf32(n_total, gran, max_bn);
     p.block_n = bn;
     if (glu) {
@@ -470,6 +498,7 @@ int conv_fwd_tf32(const sd_conv_args& a, cudaStream_t st) {
       p.cols_alloc = p.n_tiles * bn;
     }
     p.w_bytes = bn * 128;
+    p.acc_stride = (bn + 31) / 32 * 32;
     const int tail = (glu ? 2 : 1) * p.cols_alloc * 4 + (a.stats ? 8 * p.cols_alloc * 4 : 0) + 16 + 512;
     const int ring = SMEM_LIMIT - 1024 - tail;
     const int a_slot = p.planes * p.a_bytes, w_slot = p.planes * p.w_bytes;

@@ -14,7 +14,10 @@
 // split-K workspace (summed by wgrad_reduce) or straight to dw with red.global.add.
 //
 // 3xTF32: with dout_lo / in_lo given, every (sample, time block) is contracted three times -- (dy_hi, x_hi),
-// (dy_lo, x_hi), (dy_hi, x_lo) -- into the same TMEM accumulator (operands pre-split by sd_tf32_split).
+// (dy_lo, x_hi), (dy_hi, x_lo) (operands pre-split by sd_tf32_split).  The tensor core adds into its fp32 accumulator
+// with truncation (a one-sided bias of up to an ulp per MMA), so the long hi*hi chain is split: even and odd samples
+// accumulate into two separate TMEM accumulators, the two small cross passes into a third, the epilogue adds the three
+// in round-to-nearest fp32, and twice as many split-K slices are used as SMs.
 // dbias comes from an extra N=16 MMA per k-step against a constant tile of ones (passes 0 and 1: dy_hi + dy_lo).
 #include "tc_common.cuh"
 
@@ -42,7 +45,7 @@ struct WgTf32Params {
   const int* group_offsets;
   int B, T, N, K, taps, dil, G;
   long long gs, sn, sk, sj;
-  int block_c, c_atoms, n_tiles, c_tiles, nsplit, stage_bytes, passes;
+  int block_c, c_atoms, n_tiles, c_tiles, nsplit, stage_bytes, passes, acc_stride, bias_col;
   float* ws;
   float* ws_bias;
 };
@@ -135,25 +138,34 @@ conv_wgrad_tf32_kernel(const __grid_constant__ WgTf32Maps tm, const WgTf32Params
     // 8-row MMA steps of the last time block that still hold rows t < T (TMA zero-fills the rest: skip them)
     const int k_last = (p.T - (t_blocks - 1) * BLOCK_T + 7) >> 3;
     int it = 0;
+    uint32_t started = 0;          // bit a: accumulator a has been written
     for (int pass = 0; pass < p.passes; ++pass) {
       const bool bias_pass = do_bias && pass < 2;
-      int tb = 0;
+      int tb = 0, smp = 0;
       for (int i = 0; i < per_pass; ++i, ++it) {
         const int k_steps = tb == t_blocks - 1 ? k_last : BLOCK_T / 8;
-        if (++tb == t_blocks) tb = 0;
+        // 3xTF32: hi*hi of even / odd samples -> accumulators 0 / 1, the cross passes -> accumulator 2
+        const int a_idx = p.passes == 1 ? 0 : (pass == 0 ? (smp & 1) : 2);
+        // bias column sums: dy_hi of even samples -> bias accumulator 0, dy_hi of odd samples and dy_lo -> accumulator 1
+        const int b_idx = p.passes == 1 ? 0 : ((pass == 0 && !(smp & 1)) ? 0 : 1);
+        if (++tb == t_blocks) { tb = 0; ++smp; }
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t alo = smem_desc_lo(smem_base + s * p.stage_bytes, ATOM_BYTES), blo = alo + ((A_ATOMS * ATOM_BYTES) >> 4);
+          const uint32_t d = tmem_base + a_idx * p.acc_stride;
+          const bool fresh = !((started >> a_idx) & 1), fresh_b = !((started >> (4 + b_idx)) & 1);
 #pragma unroll
           for (int k = 0; k < BLOCK_T / 8; ++k) {
             if (k >= k_steps) break;
-            umma_tf32(tmem_base, desc64(alo + k * (1024 >> 4), dhi), desc64(blo + k * (1024 >> 4), dhi), idesc, (it | k) != 0);
-            if (bias_pass) umma_tf32(tmem_base + BIAS_COL, desc64(alo + k * (1024 >> 4), dhi), desc64(olo, dhi), idesc_b, (it | k) != 0);
+            umma_tf32(d, desc64(alo + k * (1024 >> 4), dhi), desc64(blo + k * (1024 >> 4), dhi), idesc, !(fresh && k == 0));
+            if (bias_pass) umma_tf32(tmem_base + p.bias_col + 16 * b_idx, desc64(alo + k * (1024 >> 4), dhi), desc64(olo, dhi), idesc_b, !(fresh_b && k == 0));
           }
           umma_commit(empty_bar(s));
           if (it == p.passes * per_pass - 1) umma_commit(tfull_bar);
         }
+        started |= 1u << a_idx;
+        if (bias_pass) started |= 1u << (4 + b_idx);
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -169,10 +181,25 @@ conv_wgrad_tf32_kernel(const __grid_constant__ WgTf32Maps tm, const WgTf32Params
     float* dwn = p.dw + (long long)g * p.gs + (long long)n * p.sn + (long long)j * p.sj;
     const int wcols = p.c_tiles * p.block_c, wrows = p.n_tiles * BLOCK_MN;
     float* wsn = p.ws ? p.ws + (((size_t)split * p.taps + j) * wrows + (n0 + quad * 32 + lane)) * wcols + c0 : nullptr;
+    const bool x3 = p.passes == 3;
+    const bool two_main = x3 && (s_end - s_begin) > 1;       // the odd-sample accumulator was written
     for (int c = ch0; c < ch1; ++c) {
       uint32_t r[16];
       tmem_ld16(taddr + c * 16, r);
-      tmem_ld_wait();
+      if (x3) {
+        uint32_t r1[16], r2[16];
+        tmem_ld16(taddr + 2 * p.acc_stride + c * 16, r2);
+        if (two_main) tmem_ld16(taddr + p.acc_stride + c * 16, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float m = __uint_as_float(r[i]);
+          if (two_main) m += __uint_as_float(r1[i]);
+          r[i] = __float_as_uint(m + __uint_as_float(r2[i]));
+        }
+      } else {
+        tmem_ld_wait();
+      }
       if (wsn) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -187,8 +214,15 @@ conv_wgrad_tf32_kernel(const __grid_constant__ WgTf32Maps tm, const WgTf32Params
     }
     if (do_bias && hsel == 0) {
       uint32_t r[16];
-      tmem_ld16(taddr + BIAS_COL, r);
-      tmem_ld_wait();
+      tmem_ld16(taddr + p.bias_col, r);
+      if (x3) {       // + the second bias accumulator (always written: it takes the dy_lo pass)
+        uint32_t r1[16];
+        tmem_ld16(taddr + p.bias_col + 16, r1);
+        tmem_ld_wait();
+        r[0] = __float_as_uint(__uint_as_float(r[0]) + __uint_as_float(r1[0]));
+      } else {
+        tmem_ld_wait();
+      }
       if (p.ws_bias) p.ws_bias[(size_t)split * wrows + n0 + quad * 32 + lane] = __uint_as_float(r[0]);
       else if (n < p.N) atomicAdd(p.dbias + n, __uint_as_float(r[0]));
     }
@@ -232,7 +266,10 @@ int conv_wgrad_tf32(const sd_wgrad_args& a, cudaStream_t st) {
   p.gs = a.gs; p.sn = a.sn; p.sk = a.sk; p.sj = a.sj;
   p.passes = a.dout_lo ? 3 : 1;
   // stage = dy tile (16 KB) + x tile (block_c/32 atoms of 4 KB); 4 stages + ones tile must fit
-  p.block_c = pick_block_c_tf32(a.Kp, 256);
+  // 3xTF32: three accumulators of block_c columns + the bias column share the 512 TMEM columns
+  p.block_c = pick_block_c_tf32(a.Kp, p.passes == 3 ? 160 : 256);
+  p.acc_stride = p.passes == 3 ? 160 : 0;
+  p.bias_col = p.passes == 3 ? 480 : BIAS_COL;
   p.c_atoms = (p.block_c + 31) / 32;
   p.n_tiles = (a.Np + BLOCK_MN - 1) / BLOCK_MN;
   p.c_tiles = (a.Kp + p.block_c - 1) / p.block_c;
@@ -240,6 +277,7 @@ int conv_wgrad_tf32(const sd_wgrad_args& a, cudaStream_t st) {
   const int sms = sm_budget();
   int nsplit = a.G > 1 ? 1 : sms / base_items;
   if (nsplit < 1) nsplit = 1;
+  if (p.passes == 3 && a.G == 1) nsplit *= 2;       // shorter accumulation chains (see the header comment)
   if (nsplit > a.B) nsplit = a.B;
   if (a.G == 1) nsplit = cdiv(a.B, cdiv(a.B, nsplit));
   p.nsplit = nsplit;

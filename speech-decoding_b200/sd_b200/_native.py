@@ -76,6 +76,7 @@ SIGNATURES = {
     "sd_collate_preproc": [vp, vp, i64, i32, i32, C.c_float, i32, vp],
     "sd_adam_step": [vp, i32, i32, f32, f32, f32, f32, vp],
     "sd_cast_rows_bf16": [vp, vp, vp, i32, i64, vp],
+    "sd_rownorm2_bf16": [vp, vp, i32, i64, vp],
     "sd_clip_coef_t_bf16": [vp, vp, i32, i32, i32, vp],
     "sd_clip_dots_tc_bf16": [vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_dz_tc_bf16": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],

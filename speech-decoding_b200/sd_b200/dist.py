@@ -164,7 +164,11 @@ def gather_speech_rows(x2d, group, allow_bf16=True, async_op=False):
     works = []
     if world > 1 and allow_bf16 and x2d.is_cuda and ops.clip_bf16_ok(x2d):
         with torch.cuda.device(x2d.device), ops.stream_scope():
-            xb, n2 = ops.cast_rows_bf16(x2d)
+            if x2d.dtype == torch.bfloat16:        # shipped in bf16 already: only the norms are missing
+                xb, n2 = x2d.contiguous(), None
+                n2 = ops.rownorm2_bf16(xb)
+            else:
+                xb, n2 = ops.cast_rows_bf16(x2d)
         pg = _PEER_GATHER.get(id(group))
         if pg is not None:
             with torch.cuda.device(x2d.device):
@@ -348,8 +352,11 @@ class DataParallel:
         world, _ = world_rank(self.group)
         if world == 1:
             return
+        from . import ops
         y2 = Y.reshape(Y.shape[0], -1)
-        if y2.dtype != torch.float32 or not y2.is_contiguous():
+        if y2.dtype == torch.bfloat16 and ops.clip_bf16_ok(y2):
+            y2 = y2.contiguous()
+        elif y2.dtype != torch.float32 or not y2.is_contiguous():
             y2 = y2.float().contiguous()
         rows, norms, works, keep = gather_speech_rows(y2, self.group, not Y.requires_grad, async_op=True)
         self.loss_fn._prefetched = (Y.data_ptr(), tuple(Y.shape), works, rows, norms, keep)

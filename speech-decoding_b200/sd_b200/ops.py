@@ -143,11 +143,12 @@ def conv_fwd(inp, w, *, K, N, taps=1, dil=1, bias=None, res=None, widx=None, G=1
 _WS = {}
 
 
-def _wgrad_workspace(device):
-    """persistent split-K scratch (64 MB) for the tensor-core wgrad kernels, one per device"""
+def _wgrad_workspace(device, mb=64):
+    """persistent split-K scratch (64 MB; 160 MB for the 3xTF32 mode, which uses twice the split-K slices) for the
+    tensor-core wgrad kernels, one per device"""
     key = (device.type, device.index)
-    if key not in _WS:
-        _WS[key] = torch.empty(16 * 1024 * 1024, dtype=torch.float32, device=device)
+    if key not in _WS or _WS[key].numel() * 4 < mb << 20:
+        _WS[key] = torch.empty(mb * 256 * 1024, dtype=torch.float32, device=device)
     return _WS[key]
 
 
@@ -164,7 +165,7 @@ def conv_wgrad(dout, inp, dw, *, K, N, taps=1, dil=1, dbias=None, order=None, of
         if tc32 == 3:
             dout, dout_lo = tf32_split(dout)
             inp, in_lo = tf32_split(inp)
-    ws = _wgrad_workspace(dout.device) if (dout.dtype == torch.bfloat16 or tc32) and G == 1 else None
+    ws = _wgrad_workspace(dout.device, 160 if tc32 == 3 else 64) if (dout.dtype == torch.bfloat16 or tc32) and G == 1 else None
     a = nat.WgradArgs(_p(dout), _p(inp), _p(dw), _p(dbias), _p(order), _p(offsets),
                       B, T, K, Kp, N, Np, taps, dil, G, strides[0], strides[1], strides[2], strides[3],
                       code, _p(ws), ws.numel() * 4 if ws is not None else 0, _p(dout_lo), _p(in_lo))
@@ -255,6 +256,14 @@ def cast_rows_bf16(x2d):
     n2 = torch.empty((M,), dtype=torch.float32, device=x2d.device)
     nat.call("sd_cast_rows_bf16", _p(x2d), _p(y), _p(n2), M, D, _st())
     return y, n2
+
+
+def rownorm2_bf16(xb):
+    """squared norms of rows that are already bf16"""
+    M, D = xb.shape
+    n2 = torch.empty((M,), dtype=torch.float32, device=xb.device)
+    nat.call("sd_rownorm2_bf16", _p(xb), _p(n2), M, D, _st())
+    return n2
 
 
 def clip_bf16_ok(x2d):

@@ -124,7 +124,11 @@ class CLIPLoss(nn.Module):
             raise NotImplementedError("sd_b200 CLIPLoss supports reduction='mean' or 'sum'")
         ops.require_cuda(x, "x")
         ops.require_cuda(y, "y")
-        xf = x.reshape(batch_size, -1).float().contiguous()
+        # speech rows that arrive in bf16 (a frozen wav2vec2 embedding rounded once on the host: half the H2D bytes) feed
+        # the bf16 similarity / gradient GEMMs as they are in the bf16 mode; every other combination computes on fp32 rows
+        x_bf16 = (x.dtype == torch.bfloat16 and not x.requires_grad and bool(fast) and ops.get_precision() == "bf16"
+                  and ops.clip_bf16_ok(x.reshape(batch_size, -1)))
+        xf = x.reshape(batch_size, -1).contiguous() if x_bf16 else x.reshape(batch_size, -1).float().contiguous()
         yf = y.reshape(batch_size, -1).float().contiguous()
         group = self.process_group
         xn2 = None
@@ -137,6 +141,9 @@ class CLIPLoss(nn.Module):
                 xf, xn2 = pre[3], pre[4]
             else:
                 xf, xn2 = sd_dist.gather_speech_rows(xf, group, not x.requires_grad)
+        elif x_bf16:
+            with torch.cuda.device(x.device), ops.stream_scope():
+                xn2 = ops.rownorm2_bf16(xf)
         zn2 = getattr(y, "_sd_norm2", None)      # set by BrainEncoder.forward (fused into its last epilogue)
         if zn2 is not None and (zn2.shape[0] != batch_size or y.dtype != torch.float32):
             zn2 = None

@@ -268,6 +268,38 @@ def test_cfg2_full_size_vs_oracle(precision, tol_out, tol_grad):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("precision,tol_out,tol_grad", [("bf16", 2e-2, 4e-2), ("tf32x3", 1e-4, 1e-4)])
+def test_cfg5_full_width_long_window_vs_oracle(precision, tol_out, tol_grad):
+    """BASELINE.json configs[4] at FULL WIDTH: T = 1200 (10 s x 120 Hz), 208 sensors, D1=270, D2=320, F=1024 -- D = F*T =
+    1,228,800 per CLIP row, 10 row tiles per sample with a ragged last tile, dilation-16 halos -- against the oracle on
+    the same GPU.  B = 64 keeps the fp32 oracle (and its two autocast runs) in seconds; the per-sample shapes are the
+    benchmarked ones (bench.py --window 1200)."""
+    args, X, Y, ids = oracle_case(B=64, C=208, T=1200, S=27, D1=270, D2=320, Fo=1024, K=32, seed=9)
+    run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad, oracle_device="cuda")
+    torch.cuda.empty_cache()
+
+
+def test_clip_accepts_bf16_speech_rows():
+    """Speech embeddings shipped in bf16 (half the host->device bytes): the bf16 mode consumes them as they are and gives
+    the loss / gradient of the same rows held in fp32."""
+    import sd_b200
+    from speech_decoding.utils.loss import CLIPLoss
+    sd_b200.set_precision("bf16")
+    torch.manual_seed(3)
+    args = restate.make_args()
+    crit = CLIPLoss(args).to(DEV)
+    B, Fo, T = 48, 64, 90
+    Yb = torch.randn(B, Fo, T, device=DEV).to(torch.bfloat16)
+    Z1 = torch.randn(B, Fo, T, device=DEV, requires_grad=True)
+    Z2 = Z1.detach().clone().requires_grad_(True)
+    l1 = crit(Yb, Z1); l1.backward()
+    l2 = crit(Yb.float(), Z2); l2.backward()
+    ref = restate.clip_loss(Yb.float().cpu(), Z1.detach().cpu(), crit.temp.detach().cpu())
+    PL.record("loss(bf16 rows vs oracle)", G.rel_err(l1, ref), 2e-2)
+    assert G.rel_err(l1, ref) < 2e-2 and G.rel_err(l2, ref) < 2e-2
+    assert G.rel_l2(Z1.grad, Z2.grad) < 2e-2
+
+
 def test_cfg2_full_size_properties():
     """BASELINE.json configs[1] at full size (B=256, 208 sensors, 360 samples, F=1024), bf16: properties that
     need no oracle -- finite outputs, BN'd activations normalised, CLIP gradient orthogonal to Z rows
