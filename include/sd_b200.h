@@ -154,6 +154,9 @@ int sd_tf32_split(const float* x, float* hi, float* lo, int64_t n, void* stream)
 /* ---- BatchNorm1d + GELU (models.py:158,161) ----------------------------------------------------- */
 /* column sums over a (rows, Cp) BTC tensor: stats[0:Cp] += sum, stats[Cp:2Cp] += sum of squares */
 int sd_colstats(const void* x, double* stats, int64_t rows, int Cp, int dtype, void* stream);
+/* out[c] += sum over the rows of x[:, c] for c < C, accumulated in fp64 (`scratch`: 2*Cp doubles, zeroed here): the conv
+ * bias gradient sum_{b,t} dout[b,t,n] of the 3xTF32 mode, which keeps this cancellation-prone sum off the tensor core */
+int sd_colsum_add(const void* x, float* out, double* scratch, int64_t rows, int C, int Cp, int dtype, void* stream);
 /* training: mean/var from stats, running-stat update (momentum, unbiased var), num_batches_tracked += 1.
  * eval: use running stats.  ss (4,Cp) fp32 = scale, shift, mean, invstd. */
 int sd_bn_finalize(const double* stats, int C, int Cp, int64_t n, const float* gamma, const float* beta,

@@ -480,6 +480,11 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(T* __restrict__ du, const
   }
 }
 
+__global__ void add_f64_to_f32_kernel(const double* __restrict__ a, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += (float)a[i];
+}
+
 static inline int ew_grid(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   const int64_t cap = 148 * 32;
@@ -558,6 +563,18 @@ int sd_colstats(const void* x, double* stats, int64_t rows, int Cp, int dtype, v
   const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
   DISPATCH_DTYPE(dtype, colreduce_kernel<T, 0><<<persistent_grid(rows, 2 * block.y, 4), block, smem, (cudaStream_t)stream>>>((T*)x, nullptr, nullptr, stats, rows, Cp));
   return check_launch("colstats");
+}
+
+int sd_colsum_add(const void* x, float* out, double* scratch, int64_t rows, int C, int Cp, int dtype, void* stream) {
+  SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048 && C <= Cp, "sd_colsum_add: bad channel counts");
+  cudaStream_t st = (cudaStream_t)stream;
+  SD_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * Cp, st));
+  dim3 block(Cp / 8, chan_block_rows(Cp));
+  const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
+  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 0><<<persistent_grid(rows, 2 * block.y, 4), block, smem, st>>>((T*)x, nullptr, nullptr, scratch, rows, Cp));
+  if (check_launch("colsum")) return 1;
+  add_f64_to_f32_kernel<<<cdiv(C, 128), 128, 0, st>>>(scratch, out, C);
+  return check_launch("colsum_add");
 }
 
 int sd_bn_finalize(const double* stats, int C, int Cp, int64_t n, const float* gamma, const float* beta,

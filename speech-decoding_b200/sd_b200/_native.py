@@ -58,6 +58,7 @@ SIGNATURES = {
     "sd_conv_fwd": [C.POINTER(ConvArgs), vp],
     "sd_conv_wgrad": [C.POINTER(WgradArgs), vp],
     "sd_colstats": [vp, vp, i64, i32, i32, vp],
+    "sd_colsum_add": [vp, vp, vp, i64, i32, i32, i32, vp],
     "sd_bn_finalize": [vp, i32, i32, i64, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp],
     "sd_bn_gelu_fwd": [vp, vp, vp, i64, i32, i32, vp],
     "sd_bn_gelu_bwd_reduce": [vp, vp, vp, vp, i64, i32, i32, vp],

@@ -167,7 +167,12 @@ class SpatialAttentionStage(Stage):
         assert C == m.spatial_dropout.num_channels                                  # models.py:78
         D1, K2 = m.z.shape
         Xt = ops.nct_to_btc(X, run.dtype)
-        mask = m.spatial_dropout.draw_mask(X.device) if m.training else None          # models.py:81-83
+        if not m.training:
+            mask = None
+        elif run.static is not None:      # CUDA-graph replay: the centre drawn by the host this step, read on the device
+            mask = run.static.dropout_mask(m.spatial_dropout, X.device)
+        else:
+            mask = m.spatial_dropout.draw_mask(X.device)                              # models.py:81-83
         z_ri = torch.view_as_real(m.z.detach())
         w_soft, w_packed = ops.sa_weights_fwd(z_ri, m.cos, m.sin, mask, D1, K2, C, run.dtype)
         out = torch.empty((B, T, rup8(D1)), dtype=run.dtype, device=X.device)
@@ -195,6 +200,13 @@ class SpatialAttentionStage(Stage):
         return None
 
 
+def subject_tables_host(ids, S):
+    """int32 [ids (B) | sample order sorted by subject (B) | group offsets (S+1)]: what the grouped GEMMs index with"""
+    order = np.argsort(ids, kind="stable").astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(ids, minlength=S))]).astype(np.int32)
+    return np.concatenate([ids.astype(np.int32), order, offsets])
+
+
 class SubjectStage(Stage):
     """1x1 conv (bias) + per-sample subject 1x1 (grouped GEMM)   models.py:113-116."""
 
@@ -217,17 +229,23 @@ class SubjectStage(Stage):
         ids = run.subject_ids
         if ids is None or len(ids) != B:
             raise RuntimeError("sd_b200: subject_idxs must have one entry per sample")
-        order = np.argsort(ids, kind="stable").astype(np.int32)
-        offsets = np.concatenate([[0], np.cumsum(np.bincount(ids, minlength=S))]).astype(np.int32)
-        host = np.concatenate([ids.astype(np.int32), order, offsets])
-        dev = torch.from_numpy(host).to(x.device, non_blocking=True)
-        widx, d_order, d_off = dev[:B], dev[B:2 * B], dev[2 * B:]
+        if run.static is not None:
+            # CUDA-graph replay: ids / order / offsets of THIS step were staged in pinned memory by the host; the copy
+            # below is a node of the graph and re-reads the staging buffer on every replay
+            widx, d_order, d_off = run.static.subject_tables(B, S, x.device)
+        else:
+            host = subject_tables_host(ids, S)
+            dev = torch.from_numpy(host).to(x.device, non_blocking=True)
+            widx, d_order, d_off = dev[:B], dev[B:2 * B], dev[2 * B:]
         h1 = torch.empty_like(x)
         ops.conv_fwd(x, run.pack.wf(self.key + ".conv"), K=D1, N=D1, bias=m.conv.bias, out=h1)
         h2 = torch.empty_like(x)
         ops.conv_fwd(h1, run.pack.wf(self.key + ".subj"), K=D1, N=D1, widx=widx, G=S, out=h2)
         if sv is not None:
-            present = np.unique(ids)
+            # which per-subject weights get a gradient: those seen in the batch (absent -> None like the reference's
+            # ModuleList); under a CUDA graph all of them do (zeros for the absent ones) and the optimizer step skips the
+            # absent entries instead (sd_b200.graph)
+            present = np.unique(ids) if run.static is None else np.arange(S)
             collect = None
             if run.host_group is not None:       # data parallel: a subject has a gradient if ANY rank saw it
                 from . import dist as sd_dist    # (exchange started here, collected in backward: the host never blocks)
@@ -495,6 +513,7 @@ class Pipeline:
         self.scratch = None
         self.out_norm2 = None       # squared row norms of the pipeline output when the last stage produced them
         self._scratch_n = sum(st.scratch for st in stages)
+        self.static = None          # graph.StaticInputs while a CUDA-graph step is being captured / replayed
         self.reducer = None         # dist.GradReducer: per-stage gradient all-reduce (data parallel)
         self.bn_group = None        # process group for SyncBN statistics, or None
         self.host_group = None      # gloo side channel for host-side metadata

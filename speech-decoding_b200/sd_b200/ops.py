@@ -163,6 +163,12 @@ def conv_wgrad(dout, inp, dw, *, K, N, taps=1, dil=1, dbias=None, order=None, of
     if tc32:
         code = nat.SD_TF32
         if tc32 == 3:
+            if dbias is not None:
+                # the bias gradient is a plain column sum with heavy cancellation: fp64 accumulation on the CUDA cores
+                # instead of the ones-tile MMA (whose truncating accumulator costs ~1e-4 here)
+                scratch = torch.empty((2 * Np,), dtype=torch.float64, device=dout.device)
+                nat.call("sd_colsum_add", _p(dout), _p(dbias), _p(scratch), B * T, N, Np, nat.SD_F32, _st())
+                dbias = None
             dout, dout_lo = tf32_split(dout)
             inp, in_lo = tf32_split(inp)
     ws = _wgrad_workspace(dout.device, 160 if tc32 == 3 else 64) if (dout.dtype == torch.bfloat16 or tc32) and G == 1 else None

@@ -53,7 +53,8 @@ def autocast_noise(sd, X, Y, ids, temp, mask, reduction="mean"):
             return restate.train_step(s2, X.to(dev), Y.to(dev), ids, temp.to(dev), None if mask is None else mask.to(dev),
                                       reduction=reduction)
     a, b = run(True), run(False)
-    out = {"Z": G.rel_l2(a["Z"].float(), b["Z"]), "loss": G.rel_err(a["loss"].float(), b["loss"]), "grads": {}}
+    out = {"Z": G.rel_l2(a["Z"].float(), b["Z"]), "loss": G.rel_err(a["loss"].float(), b["loss"]), "grads": {},
+           "dtemp": G.rel_err(a["dtemp"].float(), b["dtemp"])}
     for k, g in b["grads"].items():
         if g is not None and a["grads"][k] is not None:
             out["grads"][k] = G.rel_l2(a["grads"][k], g)
@@ -201,12 +202,13 @@ def run_vs_oracle(args, X, Y, ids, precision, tol_out, tol_grad, center=3, oracl
         tol_out = max(tol_out, 1.25 * noise["Z"])
     eZ, eL = E(Z, ref["Z"]), G.rel_err(loss, ref["loss"])
     eT = G.rel_err(crit.temp.grad, ref["dtemp"])
+    tol_temp = tol_grad if noise is None else max(tol_grad, 1.25 * noise["dtemp"])
     PL.record("Z", eZ, tol_out)
     PL.record("loss", eL, tol_out)
-    PL.record("grad:temp", eT, tol_grad)
+    PL.record("grad:temp", eT, tol_temp, **({} if noise is None else {"autocast_bf16_floor": noise["dtemp"]}))
     assert eZ < tol_out
     assert eL < tol_out
-    assert eT < tol_grad
+    assert eT < tol_temp
     worst = grad_check(enc, ref["grads"], [k for k, v in ref["grads"].items() if v is None], tol_grad, E,
                        None if noise is None else noise["grads"])
     # top-10 retrieval indices identical excluding ties (north_star)

@@ -1,0 +1,78 @@
+"""GPU: the CUDA-graph training step (sd_b200.graph.GraphedTrainStep, SURVEY 8f rank 3 / train.py:187-203) against the
+eager step  Z = enc(X, ids); loss = crit(Y, Z); zero_grad; backward; FusedAdam.step  on identical replicas: same
+losses, parameters, BatchNorm buffers and optimizer state after several steps with changing inputs, changing subject
+sets (absent subjects must stay untouched, like `grad None` under torch.optim.Adam) and changing dropout centres."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate
+from tests import golden_util as G
+from tests import parity_log as PL
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _build(args, seed):
+    from sd_b200.optim import FusedAdam
+    from speech_decoding.models import BrainEncoder
+    from speech_decoding.utils.loss import CLIPLoss
+    torch.manual_seed(seed)
+    enc, crit = BrainEncoder(args).to(DEV).train(), CLIPLoss(args).to(DEV).train()
+    opt = FusedAdam(list(enc.parameters()) + list(crit.parameters()), lr=1e-3)
+    return enc, crit, opt
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-3)])
+def test_graphed_step_matches_eager_steps(precision, tol):
+    import sd_b200
+    from sd_b200.graph import GraphedTrainStep
+    sd_b200.set_precision(precision)
+    S, B, C, T, Fo = 7, 16, 24, 96, 64
+    args = restate.make_args(D1=40, D2=48, F_=Fo, K=4, num_subjects=S, num_channels=C, last4layers=False)
+    enc_e, crit_e, opt_e = _build(args, 5)
+    enc_g, crit_g, opt_g = _build(args, 5)
+    g = torch.Generator().manual_seed(11)
+    batches = []
+    for i in range(5):
+        ids = torch.randint(0, S - 2 if i % 2 else S, (B,), generator=g, dtype=torch.int32)    # subjects 5, 6 absent on odd steps
+        batches.append((torch.randn(B, C, T, generator=g).clamp(-20, 20).to(DEV), torch.randn(B, Fo, T, generator=g).to(DEV), ids))
+    np.random.seed(21)
+    step = GraphedTrainStep(enc_g, crit_g, opt_g, *batches[0])
+    # capture must leave no trace
+    for (k, a), (_, b) in zip(enc_e.state_dict().items(), enc_g.state_dict().items()):
+        assert torch.equal(torch.view_as_real(a) if a.is_complex() else a, torch.view_as_real(b) if b.is_complex() else b), k
+    np.random.seed(33)
+    losses_g = [float(step(X, Y, ids)) for X, Y, ids in batches]
+    np.random.seed(33)
+    losses_e = []
+    for X, Y, ids in batches:
+        Z = enc_e(X, ids)
+        loss = crit_e(Y, Z)
+        opt_e.zero_grad(set_to_none=True)
+        loss.backward()
+        opt_e.step()
+        losses_e.append(float(loss.detach()))
+    worst = 0.0
+    for a, b in zip(losses_g, losses_e):
+        worst = max(worst, abs(a - b) / abs(b))
+    PL.record("loss(graph vs eager)", worst, tol)
+    assert worst < tol, (losses_g, losses_e)
+    worst_p = ("", 0.0)
+    sd_e, sd_g = enc_e.state_dict(), enc_g.state_dict()
+    for k in sd_e:
+        e = G.rel_err(sd_g[k].float() if not sd_g[k].is_complex() else sd_g[k], sd_e[k].float() if not sd_e[k].is_complex() else sd_e[k], floor=1e-3)
+        if e > worst_p[1]:
+            worst_p = (k, e)
+        assert e < 10 * tol, (k, e)
+    PL.record("state_dict(graph vs eager)", worst_p[1], 10 * tol, worst_param=worst_p[0])
+    assert int(sd_g["conv_blocks.conv0.batchnorm0.num_batches_tracked"]) == 5
+    assert G.rel_err(crit_g.temp, crit_e.temp) < 10 * tol
+    # optimizer state: the weights of subjects 5 and 6 were updated on the even steps only
+    for s in range(S):
+        pe, pg = enc_e.subject_block.subject_layer[s].weight, enc_g.subject_block.subject_layer[s].weight
+        assert float(opt_g.state[pg]["step"]) == float(opt_e.state[pe]["step"]), s
+    assert float(opt_g.state[enc_g.subject_block.subject_layer[6].weight]["step"]) < 5
