@@ -363,7 +363,8 @@ def run_ours(a, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     value = world * B / (ms / 1e3)
-    loss_val = float(loss)
+    loss_val = float(loss.detach())
+    del loss          # (no eager autograd graph may outlive this point: the CUDA-graph capture below needs fresh accumulators)
 
     # ---- roofline of the dominant kernel (tcgen05 conv fwd/dgrad), CUDA events around each launch ----
     roof = None
@@ -416,18 +417,33 @@ def run_ours(a, rank, world, local_rank):
             bufs[i][1].copy_(Yh, non_blocking=True)
             evs[i].record(copy_stream)
 
+    graphed = None
+    if world == 1 and a.graph:
+        # the whole step (forward, CLIP loss, backward, fused Adam) as ONE CUDA graph (sd_b200.graph)
+        from sd_b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(enc, crit, opt, X, Y, ids)
+
     def e2e_loop(n):
         prefetch(0)
         last = None
         for i in range(n):
             cur = i & 1
-            if i + 1 < n:
-                prefetch(cur ^ 1)
             torch.cuda.current_stream().wait_event(evs[cur])
             Xd, Yd = bufs[cur]
+            if graphed is not None:
+                steps_seen[0] += 1
+                loss = graphed(Xd, Yd, ids)
+                if i + 1 < n:
+                    prefetch(cur ^ 1)                  # next batch: H2D on the copy stream while the graph runs
+                last = loss.item()                     # D2H read of the step's result (train.py:196)
+                continue
             if dp is not None:
                 dp.prefetch_targets(Yd)
             Z = enc(Xd, ids)
+            if i + 1 < n:
+                # next batch: issued after the encoder's own small uploads (subject ids) so that those do not queue on the
+                # H2D copy engine behind this 265 MB transfer
+                prefetch(cur ^ 1)
             loss = crit(Yd, Z)
             opt.zero_grad(set_to_none=True)
             loss.backward()
@@ -470,7 +486,8 @@ def run_ours(a, rank, world, local_rank):
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 3),
                     "h2d_bytes_per_step": int(Xh.numel() * Xh.element_size() + Yh.numel() * Yh.element_size()), "d2h_bytes_per_step": 4,
                     "includes": "H2D of X (fp32) and Y (%s) from pinned memory (double-buffered on a copy stream), fwd, loss, backward, "
-                                "fused Adam step (sd_adam_step), loss.item()" % ("bf16" if y_bf16 else "fp32")},
+                                "fused Adam step (sd_adam_step), loss.item()%s" % ("bf16" if y_bf16 else "fp32",
+                                "; the step is replayed as one CUDA graph (sd_b200.graph.GraphedTrainStep)" if graphed is not None else "")},
             "gpu_launches": launches, "clocks": clk}
     if dp is not None:
         red = enc.pipeline().reducer
@@ -496,6 +513,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3", "fp32"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--sync-bn", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=1, help="e2e leg at 1 GPU: replay the step as one CUDA graph")
     ap.add_argument("--speech-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="storage of the (frozen) speech embeddings Y in the bf16 mode")
     ap.add_argument("--window", type=int, default=CFG["T"],

@@ -279,6 +279,10 @@ int sd_ipc_get_handle(void* ptr, void* handle_out);
 int sd_ipc_open_handle(const void* handle, void** ptr_out);
 int sd_ipc_close_handle(void* ptr);
 int sd_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
+/* dst (device) <- src, up to 4 MB, by a KERNEL.  src may be pinned host memory (device-addressable under unified
+ * addressing): the per-step integer tables and the Adam table of the CUDA-graph step (train.py:187-203 as one graph) are
+ * fetched this way so that they never queue on the host-to-device copy engine behind the bulk transfer of the next batch */
+int sd_copy_small(void* dst, const void* src, int64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,24 @@
 
 using namespace sd;
 
+namespace sd {
+// src may be PINNED HOST memory (directly addressable from the device under unified addressing): the SMs read it over
+// PCIe themselves, so the copy does not queue on the host-to-device copy engine behind a bulk input transfer
+__global__ void copy_small_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace sd
+
 extern "C" {
+
+int sd_copy_small(void* dst, const void* src, int64_t bytes, void* stream) {
+  SD_REQUIRE(dst && src && bytes >= 0 && bytes % 4 == 0 && bytes <= (1 << 22) && !(((uintptr_t)dst | (uintptr_t)src) & 3),
+             "sd_copy_small: up to 4 MB, 4-byte granular");
+  if (bytes == 0) return 0;
+  const int n = (int)(bytes / 4);
+  copy_small_kernel<<<n > 4096 ? 16 : 1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(src), n);
+  return check_launch("copy_small");
+}
 
 int sd_peer_alloc(void** ptr, int64_t bytes) {
   SD_REQUIRE(ptr != nullptr && bytes > 0, "sd_peer_alloc: bad arguments");

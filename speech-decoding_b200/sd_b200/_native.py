@@ -90,6 +90,7 @@ SIGNATURES = {
     "sd_ipc_open_handle": [vp, C.POINTER(vp)],
     "sd_ipc_close_handle": [vp],
     "sd_memcpy_async": [vp, vp, i64, vp],
+    "sd_copy_small": [vp, vp, i64, vp],
 }
 
 _lib = None

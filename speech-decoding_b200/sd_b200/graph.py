@@ -65,8 +65,10 @@ class StaticInputs:
         self._copied = False
 
     def _ensure_copied(self):
-        if not self._copied:                     # ONE copy node per step, issued by whichever stage asks first
-            self.dev.copy_(self.host, non_blocking=True)
+        if not self._copied:                     # ONE copy per step, issued by whichever stage asks first: a kernel that reads
+            # the pinned buffer itself (a memcpy node would queue on the H2D copy engine behind the next batch's transfer)
+            with ops.stream_scope():
+                nat.call("sd_copy_small", self.dev.data_ptr(), self.host.data_ptr(), self.host.numel() * 4, ops._st())
             self._copied = True
 
     def subject_tables(self, B, S, device):
@@ -129,6 +131,13 @@ class GraphedTrainStep:
         return loss
 
     def _capture(self, subject_idxs, warmup):
+        # autograd binds every parameter's gradient accumulator to the stream that was current when the accumulator was
+        # created, and keeps it alive as long as ANY graph that used it is alive (e.g. a loss tensor of an earlier
+        # eager step that the caller still holds).  Accumulators bound to the default (legacy) stream would pull that
+        # stream into the capture and invalidate it, so stale graphs are collected first and the warm-up below -- on a
+        # side stream, as for any whole-network capture -- creates fresh ones.
+        import gc
+        gc.collect()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         rng = np.random.get_state()
@@ -151,9 +160,18 @@ class GraphedTrainStep:
         np.random.set_state(rng)
         self._adam_init()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self.loss = self._body(ids)
-            self._adam_enqueue()
+        try:
+            with torch.cuda.graph(self._graph):
+                self.loss = self._body(ids)
+                self._adam_enqueue()
+        except RuntimeError as e:
+            if "legacy stream" in str(e) or "capture" in str(e).lower():
+                raise RuntimeError(
+                    "GraphedTrainStep: stream capture failed (%s).  The usual cause: a tensor produced by an earlier EAGER "
+                    "training step of these modules (typically the last `loss`, or Z) is still alive; its autograd graph "
+                    "keeps the parameters' gradient accumulators bound to the default stream.  Drop those tensors (del "
+                    "loss, Z) before constructing GraphedTrainStep." % str(e).splitlines()[0]) from e
+            raise
         self._restore(snapshot)                         # (capturing does not execute, but keep the contract obvious)
         self.loss = self.loss.detach()
 
@@ -177,7 +195,7 @@ class GraphedTrainStep:
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             self.adam_params.append(p)
         k = len(self.adam_params)
-        nbytes = k * ctypes.sizeof(nat.AdamEntry)
+        nbytes = (k * ctypes.sizeof(nat.AdamEntry) + 3) // 4 * 4
         self._adam_host = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
         self._adam_dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         self._adam_max_n = max((2 if p.is_complex() else 1) * p.numel() for p in self.adam_params)
@@ -197,7 +215,7 @@ class GraphedTrainStep:
                                   real(st["exp_avg_sq"]).data_ptr(), real(p).numel()))
         beta1, beta2 = self.group["betas"]
         with torch.cuda.device(self.device), ops.stream_scope():
-            self._adam_dev.copy_(self._adam_host, non_blocking=True)
+            nat.call("sd_copy_small", self._adam_dev.data_ptr(), self._adam_host.data_ptr(), self._adam_host.numel(), ops._st())
             nat.call("sd_adam_step", self._adam_dev.data_ptr(), len(self._entries), min(1024, (self._adam_max_n + 1023) // 1024),
                      float(beta1), float(beta2), float(self.group["eps"]), float(self.group["weight_decay"]), ops._st())
 
