@@ -279,6 +279,9 @@ int sd_ipc_get_handle(void* ptr, void* handle_out);
 int sd_ipc_open_handle(const void* handle, void** ptr_out);
 int sd_ipc_close_handle(void* ptr);
 int sd_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
+/* arrival fence of the copy-engine gather: returns (in stream order) once flags[0..world) all equal `expected`; every peer
+ * writes its flag after its rows.  Traps after 10 s instead of hanging. */
+int sd_peer_wait_flags(const int* flags, int world, int expected, void* stream);
 /* dst (device) <- src, up to 4 MB, by a KERNEL.  src may be pinned host memory (device-addressable under unified
  * addressing): the per-step integer tables and the Adam table of the CUDA-graph step (train.py:187-203 as one graph) are
  * fetched this way so that they never queue on the host-to-device copy engine behind the bulk transfer of the next batch */

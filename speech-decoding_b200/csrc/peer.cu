@@ -14,9 +14,41 @@ namespace sd {
 __global__ void copy_small_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
+// Arrival fence of the copy-engine all-gather: every peer writes `expected` into its flag word of this rank's receive
+// buffer AFTER its rows (same stream, so the copy engine has completed the rows first).  One thread per peer polls; the
+// kernel boundary orders the CLIP kernels that follow in the stream after the rows' arrival.  An SM-resident NCCL
+// collective as the fence would have to find a free SM next to back-to-back persistent 148-CTA grids (measured: it is
+// starved for the whole encoder forward); this kernel is an ordinary in-stream launch.
+__global__ void peer_wait_kernel(const int* flags, int world, int expected) {
+  const int i = threadIdx.x;
+  if (i < world) {
+    const volatile int* f = flags + i;
+    uint64_t t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (uint32_t spin = 0; *f != expected; ++spin) {
+      __nanosleep(200);
+      if ((spin & 0xfff) == 0xfff) {
+        uint64_t t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) {   // 10 s: a peer died or the protocol is broken -- abort instead of hanging
+          printf("sd_b200: peer gather fence timed out (peer %d: flag %d, expected %d)\n", i, *f, expected);
+          __trap();
+        }
+      }
+    }
+  }
+  __threadfence_system();
+}
+
 }  // namespace sd
 
 extern "C" {
+
+int sd_peer_wait_flags(const int* flags, int world, int expected, void* stream) {
+  SD_REQUIRE(flags && world > 0 && world <= 64, "sd_peer_wait_flags: bad arguments");
+  peer_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(flags, world, expected);
+  return check_launch("peer_wait_flags");
+}
 
 int sd_copy_small(void* dst, const void* src, int64_t bytes, void* stream) {
   SD_REQUIRE(dst && src && bytes >= 0 && bytes % 4 == 0 && bytes <= (1 << 22) && !(((uintptr_t)dst | (uintptr_t)src) & 3),

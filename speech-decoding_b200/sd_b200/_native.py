@@ -91,6 +91,7 @@ SIGNATURES = {
     "sd_ipc_close_handle": [vp],
     "sd_memcpy_async": [vp, vp, i64, vp],
     "sd_copy_small": [vp, vp, i64, vp],
+    "sd_peer_wait_flags": [vp, i32, i32, vp],
 }
 
 _lib = None

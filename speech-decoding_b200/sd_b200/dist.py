@@ -46,17 +46,32 @@ class _RawDeviceBuffer:
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
 
 
+class _PeerArrival:
+    """Work-like handle of one copy-engine gather: wait() orders the current stream after the arrival of every peer's rows."""
+
+    def __init__(self, flags_ptr, world, expected, device):
+        self.flags_ptr, self.world, self.expected, self.device = flags_ptr, world, expected, device
+
+    def wait(self):
+        from . import _native as nat
+        with torch.cuda.device(self.device):
+            nat.call("sd_peer_wait_flags", self.flags_ptr, self.world, self.expected, torch.cuda.current_stream().cuda_stream)
+
+
 class PeerGather:
-    """All-gather of the bf16 speech rows on the COPY ENGINES: every rank owns a receive buffer (two parity slots of
-    world x rows x D bf16, allocated by the native library so that it has a CUDA IPC handle), peers map it once and each
-    step PUSH their rows into their slot with peer cudaMemcpyAsync on side streams.  No SM is occupied, so the transfer
-    overlaps the persistent tcgen05 grids of the encoder forward without costing them a wave (an NCCL all-gather kernel
-    holds SMs for the whole 1.3 GB transfer at 8 GPUs).  The tiny NCCL all-gather of the row norms that follows the
-    pushes in stream order is also the arrival fence: when it completes on a rank, every peer's push has landed.
-    Slot reuse is safe with two slots because consecutive steps are separated by a collective every rank takes part in
-    (row-statistics all-reduce in the loss, gradient all-reduce in backward)."""
+    """All-gather of the bf16 speech rows (and their squared norms) on the COPY ENGINES: every rank owns a receive buffer
+    (two parity slots of [world x rows x D bf16 | world x rows fp32 norms | world flag words], allocated by the native
+    library so that it has a CUDA IPC handle), peers map it once and each step PUSH their rows, norms and -- last, on the
+    same stream -- an arrival flag into their part of it with peer cudaMemcpyAsync on side streams.  No SM is occupied and
+    no NCCL kernel takes part: the transfer overlaps the persistent tcgen05 grids of the encoder forward without costing
+    them a wave (an NCCL all-gather kernel holds SMs for the whole 1.3 GB transfer at 8 GPUs, and even a tiny NCCL
+    collective used as the arrival fence is starved of an SM by back-to-back 148-CTA grids -- both measured,
+    tools/dist_phases.py).  The consumer's side of the fence is one polling kernel in stream order
+    (sd_peer_wait_flags).  Slot reuse is safe with two slots because consecutive steps are separated by a collective
+    every rank takes part in (row-statistics exchange in the loss, gradient all-reduce in backward)."""
 
     NSTREAMS = 4
+    NCONST = 1024
 
     def __init__(self, group, host_group, device):
         self.group, self.host_group, self.device = group, host_group, torch.device(device)
@@ -66,8 +81,8 @@ class PeerGather:
         self.peers = None            # device pointers of every rank's receive buffer, mapped into this process
         self.step = 0
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.NSTREAMS)]
-        self.events = [torch.cuda.Event() for _ in range(self.NSTREAMS)]
         self.ready = torch.cuda.Event()
+        self.consts = torch.arange(1, self.NCONST + 1, dtype=torch.int32, device=self.device)    # flag values to copy from
         self.timing = None           # tools/dist_phases.py: list of (start, end) timing events of the pushes, per call
 
     def _release(self):
@@ -85,7 +100,10 @@ class PeerGather:
         from . import _native as nat
         torch.cuda.synchronize(self.device)
         self._release()
-        self.slot_bytes = self.world * rows * D * 2
+        self.rows_bytes = self.world * rows * D * 2
+        self.norm_off = (self.rows_bytes + 255) // 256 * 256
+        self.flag_off = self.norm_off + (self.world * rows * 4 + 255) // 256 * 256
+        self.slot_bytes = self.flag_off + 256
         base = ctypes.c_void_p()
         nat.call("sd_peer_alloc", ctypes.byref(base), 2 * self.slot_bytes)
         self.base = base.value
@@ -107,25 +125,32 @@ class PeerGather:
                 nat.call("sd_ipc_open_handle", ctypes.create_string_buffer(h, len(h)), ctypes.byref(out))
                 self.peers.append(out.value)
         flat = torch.as_tensor(_RawDeviceBuffer(self.base, 2 * self.slot_bytes), device=self.device)
-        self.slots = [flat[i * self.slot_bytes:(i + 1) * self.slot_bytes].view(torch.bfloat16).view(self.world * rows, D)
-                      for i in range(2)]
+        flat.zero_()                                   # flag words start at 0 (never a valid flag value)
+        self.row_views, self.norm_views = [], []
+        for i in range(2):
+            sl = flat[i * self.slot_bytes:(i + 1) * self.slot_bytes]
+            self.row_views.append(sl[:self.rows_bytes].view(torch.bfloat16).view(self.world * rows, D))
+            self.norm_views.append(sl[self.norm_off:self.norm_off + self.world * rows * 4].view(torch.float32))
         self.shape = (rows, D)
-        dist.barrier(group=self.host_group)     # nobody pushes before everybody has mapped
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.host_group)     # nobody pushes before everybody has mapped and zeroed
 
     def gather(self, xb, n2):
-        """xb (rows, D) bf16, n2 (rows,) fp32, both produced on the current stream -> (all rows, all norms, works)."""
+        """xb (rows, D) bf16, n2 (rows,) fp32, both produced on the current stream -> (all rows, all norms, [arrival])."""
         from . import _native as nat
         rows, D = xb.shape
         if self.shape != (rows, D):
             self._setup(rows, D)
         slot = self.step & 1
+        expected = self.step % self.NCONST + 1
         self.step += 1
         nbytes = rows * D * 2
-        off = slot * self.slot_bytes + self.rank * nbytes
+        base = slot * self.slot_bytes
         self.ready.record()
         t_ev = None
         if self.timing is not None:
             t_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        flag_src = self.consts.data_ptr() + 4 * (expected - 1)
         for k in range(self.world):               # k = 0 is the local slot; peers in ring order so that no two ranks
             peer = (self.rank + k) % self.world   # push into the same destination at the same time
             st = self.streams[k % self.NSTREAMS]
@@ -133,17 +158,22 @@ class PeerGather:
                 st.wait_event(self.ready)
                 if k == 0 and t_ev is not None:
                     t_ev[0].record(st)
-            nat.call("sd_memcpy_async", self.peers[peer] + off, xb.data_ptr(), nbytes, st.cuda_stream)
-        for i in range(1, min(self.NSTREAMS, self.world)):
-            self.events[i].record(self.streams[i])
-            self.streams[0].wait_event(self.events[i])
+            if k < self.NSTREAMS:             # the side streams read xb / n2 after this call returns: the caching allocator
+                xb.record_stream(st)          # must not hand their memory out again before those streams are past the copies
+                n2.record_stream(st)
+            dst = self.peers[peer] + base
+            nat.call("sd_memcpy_async", dst + self.rank * nbytes, xb.data_ptr(), nbytes, st.cuda_stream)
+            nat.call("sd_memcpy_async", dst + self.norm_off + self.rank * rows * 4, n2.data_ptr(), rows * 4, st.cuda_stream)
+            nat.call("sd_memcpy_async", dst + self.flag_off + self.rank * 4, flag_src, 4, st.cuda_stream)   # after the data
         if t_ev is not None:
+            for i in range(1, min(self.NSTREAMS, self.world)):
+                ev = torch.cuda.Event()
+                ev.record(self.streams[i])
+                self.streams[0].wait_event(ev)
             t_ev[1].record(self.streams[0])
             self.timing.append(t_ev)
-        norms = torch.empty((self.world * rows,), dtype=n2.dtype, device=n2.device)
-        with torch.cuda.stream(self.streams[0]):
-            work = dist.all_gather_into_tensor(norms, n2, group=self.group, async_op=True)
-        return self.slots[slot], norms, [work]
+        arrival = _PeerArrival(self.base + base + self.flag_off, self.world, expected, self.device)
+        return self.row_views[slot], self.norm_views[slot], [arrival]
 
     def __del__(self):
         try:

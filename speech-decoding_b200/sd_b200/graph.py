@@ -220,23 +220,38 @@ class GraphedTrainStep:
                      float(beta1), float(beta2), float(self.group["eps"]), float(self.group["weight_decay"]), ops._st())
 
     def _adam_table(self, ids):
-        """host side of the update for THIS step: step counts, bias corrections, absent subjects skipped.  Built in a
-        shadow table; __call__ moves it into the pinned buffer once the previous replay has finished with that."""
+        """host side of the update for THIS step: step counts, bias corrections, absent subjects skipped.  Built (numpy,
+        vectorised over the ~100 entries) in a shadow table; __call__ moves it into the pinned buffer once the previous
+        replay has finished with that."""
         beta1, beta2 = self.group["betas"]
         lr = self.group["lr"]
-        present = set(int(s) for s in np.unique(ids))
         if getattr(self, "_adam_shadow", None) is None:
-            self._adam_shadow = (nat.AdamEntry * len(self._entries))()
-        table = self._adam_shadow
-        for i, (p, e) in enumerate(zip(self.adam_params, self._entries)):
-            s = self.subject_param_index.get(id(p))
-            if s is not None and s not in present:
-                table[i] = nat.AdamEntry(e[0], e[1], e[2], e[3], 0, 0.0, 1.0)          # grad None in eager mode: untouched
-                continue
-            st = self.opt.state[p]
-            st["step"] += 1
-            step = float(st["step"])
-            table[i] = nat.AdamEntry(e[0], e[1], e[2], e[3], e[4], lr / (1.0 - beta1 ** step), math.sqrt(1.0 - beta2 ** step))
+            k = len(self._entries)
+            dt = np.dtype([("param", "<u8"), ("grad", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"),
+                           ("step_size", "<f4"), ("bc2", "<f4")])
+            assert dt.itemsize == ctypes.sizeof(nat.AdamEntry)
+            self._adam_shadow = np.zeros(k, dtype=dt)
+            for i, e in enumerate(self._entries):
+                self._adam_shadow[i] = (e[0], e[1], e[2], e[3], e[4], 0.0, 1.0)
+            self._adam_n = np.array([e[4] for e in self._entries], dtype=np.int64)
+            self._adam_subject = np.array([self.subject_param_index.get(id(p), -1) for p in self.adam_params], dtype=np.int64)
+            self._adam_steps = np.array([float(self.opt.state[p]["step"]) for p in self.adam_params], dtype=np.float64)
+        present = np.zeros(self.S + 1, dtype=bool)
+        present[np.unique(ids)] = True
+        present[self.S] = True                                           # index -1: not a per-subject weight
+        active = present[self._adam_subject]
+        self._adam_steps += active                                       # grad None in eager mode: step count untouched
+        t = self._adam_shadow
+        t["n"] = np.where(active, self._adam_n, 0)                       # ... and a zero-length entry: nothing is written
+        t["step_size"] = lr / (1.0 - beta1 ** self._adam_steps)
+        t["bc2"] = np.sqrt(1.0 - beta2 ** self._adam_steps)
+        self._steps_dirty = True
+
+    def sync_optimizer_state(self):
+        """write the step counts kept by the graph back into optimizer.state (state_dict() / checkpointing)"""
+        if getattr(self, "_adam_shadow", None) is not None:
+            for p, st in zip(self.adam_params, self._adam_steps):
+                self.opt.state[p]["step"].fill_(float(st))
 
     # ---- public ---------------------------------------------------------------------------------------------
     def __call__(self, X, Y, subject_idxs):
@@ -254,7 +269,7 @@ class GraphedTrainStep:
         # ... then the previous replay must have consumed the pinned staging buffers before they are rewritten
         torch.cuda.current_stream(self.device).synchronize()
         self.static.publish(tab)
-        ctypes.memmove(self._adam_host.data_ptr(), ctypes.addressof(self._adam_shadow), ctypes.sizeof(self._adam_shadow))
+        ctypes.memmove(self._adam_host.data_ptr(), self._adam_shadow.ctypes.data, self._adam_shadow.nbytes)
         if X.data_ptr() != self.X.data_ptr():
             self.X.copy_(X, non_blocking=True)
         if Y.data_ptr() != self.Y.data_ptr():

@@ -88,6 +88,7 @@ def test_graphed_step_matches_eager_steps(precision, tol):
     assert int(sd_g["conv_blocks.conv0.batchnorm0.num_batches_tracked"]) == 5
     assert precision != "fp32" or G.rel_err(crit_g.temp, crit_e.temp) < 10 * tol
     # optimizer state: the weights of subjects 5 and 6 were updated on the even steps only
+    step.sync_optimizer_state()
     for s in range(S):
         pe, pg = enc_e.subject_block.subject_layer[s].weight, enc_g.subject_block.subject_layer[s].weight
         assert float(opt_g.state[pg]["step"]) == float(opt_e.state[pe]["step"]), s
