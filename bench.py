@@ -318,12 +318,21 @@ def run_ours(a, rank, world, local_rank):
 
     steps_seen = [0]
 
+    # Data parallel: the speech rows of the NEXT step are exchanged while this step's backward runs (they are input data:
+    # a prefetching loader has them one step ahead) -- software pipelining of the one bulk exchange of the path; each
+    # step still contains exactly one gather.  --dp-pipeline 0 starts it at the top of the same step instead.
+    pipelined = dp is not None and bool(a.dp_pipeline)
+    if pipelined:
+        dp.prefetch_targets(Y)
+
     def hot_step():
         steps_seen[0] += 1
-        if dp is not None:
+        if dp is not None and not pipelined:
             dp.prefetch_targets(Y)          # Y all-gather overlaps the encoder forward
         Z = enc(X, ids)
         loss = crit(Y, Z)
+        if pipelined:
+            dp.prefetch_targets(Y)          # next step's rows: overlaps backward (copy engines, no SM)
         for p in opt.param_groups[0]["params"]:
             p.grad = None
         loss.backward()
@@ -417,6 +426,7 @@ def run_ours(a, rank, world, local_rank):
             bufs[i][1].copy_(Yh, non_blocking=True)
             evs[i].record(copy_stream)
 
+    gather_stream = torch.cuda.Stream(device=dev)
     graphed = None
     if world == 1 and a.graph:
         # the whole step (forward, CLIP loss, backward, fused Adam) as ONE CUDA graph (sd_b200.graph)
@@ -437,7 +447,7 @@ def run_ours(a, rank, world, local_rank):
                     prefetch(cur ^ 1)                  # next batch: H2D on the copy stream while the graph runs
                 last = loss.item()                     # D2H read of the step's result (train.py:196)
                 continue
-            if dp is not None:
+            if dp is not None and (not pipelined or i == 0):
                 dp.prefetch_targets(Yd)
             Z = enc(Xd, ids)
             if i + 1 < n:
@@ -445,6 +455,12 @@ def run_ours(a, rank, world, local_rank):
                 # H2D copy engine behind this 265 MB transfer
                 prefetch(cur ^ 1)
             loss = crit(Yd, Z)
+            if pipelined and i + 1 < n:
+                # next step's speech rows: as soon as their H2D copy has landed, on a side stream (norms + peer pushes),
+                # so that the main stream never waits for the transfer
+                with torch.cuda.stream(gather_stream):
+                    gather_stream.wait_event(evs[cur ^ 1])
+                    dp.prefetch_targets(bufs[cur ^ 1][1])
             opt.zero_grad(set_to_none=True)
             loss.backward()
             steps_seen[0] += 1
@@ -493,6 +509,8 @@ def run_ours(a, rank, world, local_rank):
         red = enc.pipeline().reducer
         line["config"]["data_parallel"] = {
             "speech_row_gather": "copy-engine push into CUDA-IPC peer buffers (no SM)" if dp.peer is not None else "NCCL all-gather",
+            "speech_row_gather_schedule": "next step's rows, during this step's backward" if pipelined else "this step's rows, during the encoder forward",
+            "small_exchanges": "one-kernel all-gather through peer memory (sd_peer_exchange)" if dp.mailbox is not None else "NCCL all-reduce",
             "grad_allreduce_launches_per_step": round(red.launched / max(1, steps_seen[0]), 2),
             "numa_bound_cpus": numa_cpus}
     if roof:
@@ -513,6 +531,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3", "fp32"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--sync-bn", type=int, default=0)
+    ap.add_argument("--dp-pipeline", type=int, default=1,
+                    help="N>1: exchange the next step's speech rows during this step's backward (1) or this step's during its forward (0)")
     ap.add_argument("--graph", type=int, default=1, help="e2e leg at 1 GPU: replay the step as one CUDA graph")
     ap.add_argument("--speech-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="storage of the (frozen) speech embeddings Y in the bf16 mode")

@@ -233,6 +233,9 @@ int sd_clip_dz_tc(const float* coef_t, const float* cz, const float* x, const fl
 int sd_cast_rows_bf16(const float* x, void* y, float* nrm2, int M, int64_t D, void* stream);
 /* squared norms of rows that already are bf16 (M, D), D % 8 == 0: speech embeddings shipped from the host in bf16 */
 int sd_rownorm2_bf16(const void* x, float* nrm2, int M, int64_t D, void* stream);
+/* gathered (world, M, 2) per-rank row statistics (max_j, sum_j exp(l - max)) over each rank's columns -> row_lse (M) over all
+ * columns (loss.py:79 with global-batch negatives); world = 1 finishes the single-GPU statistics */
+int sd_clip_merge_row_stats(const float* gathered, int world, int M, float* row_lse, void* stream);
 int sd_clip_coef_t_bf16(const float* coef, void* coef_t, int M, int N, int Mp, void* stream);
 int sd_clip_dots_tc_bf16(const void* x, const void* z, float* dots, void* workspace, int M, int N, int64_t D,
                          void* stream);
@@ -282,6 +285,16 @@ int sd_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 /* arrival fence of the copy-engine gather: returns (in stream order) once flags[0..world) all equal `expected`; every peer
  * writes its flag after its rows.  Traps after 10 s instead of hanging. */
 int sd_peer_wait_flags(const int* flags, int world, int expected, void* stream);
+/* Small all-gather through peer memory in ONE kernel: this rank's `bytes` (multiple of 4, <= cap_bytes) are stored into its
+ * row of every peer's mailbox over NVLink, the epoch is published, the peers' epochs are awaited, and the world rows are
+ * copied to `gathered` (world x bytes).  Mailbox (sd_peer_alloc, zero-filled, IPC-mapped by every peer):
+ * [2][world][cap_bytes] payload followed by [2][world] int32 flags; peers_dev = device array of the world mailbox pointers
+ * as mapped into THIS process; epoch = 1, 2, 3, ... in lock-step on all ranks.  Replaces the latency-bound NCCL
+ * all-reduces of the data-parallel step (SyncBN statistics, CLIP row statistics, loss partials). */
+int sd_peer_exchange(const void* src, int64_t bytes, void* const* peers_dev, int rank, int world, int64_t cap_bytes, int epoch,
+                     void* gathered, void* stream);
+/* out[i] = sum over q < world of in[q][i], in rank order (fp32 or fp64): the reduction of a gathered exchange */
+int sd_sum_rows(const void* in, void* out, int world, int n, int is_f64, void* stream);
 /* dst (device) <- src, up to 4 MB, by a KERNEL.  src may be pinned host memory (device-addressable under unified
  * addressing): the per-step integer tables and the Adam table of the CUDA-graph step (train.py:187-203 as one graph) are
  * fetched this way so that they never queue on the host-to-device copy engine behind the bulk transfer of the next batch */

@@ -371,6 +371,25 @@ int sd_cast_rows_bf16(const float* x, void* y, float* nrm2, int M, int64_t D, vo
   return check_launch("cast_rows_bf16");
 }
 
+// row_lse[i] = log sum_j exp(logit[i][j]) over the columns of ALL ranks from the per-rank (max, sum exp(l - max)) pairs
+// (world == 1: just max + log(sum)); replaces the max / sum all-reduces and the eager exp / mul / log glue of loss.py:79's
+// cross-entropy over global-batch negatives
+__global__ void clip_merge_rows_kernel(const float* __restrict__ g, int world, int M, float* __restrict__ row_lse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float m = g[2 * i];
+  for (int q = 1; q < world; ++q) m = fmaxf(m, g[((size_t)q * M + i) * 2]);
+  float s = 0.f;
+  for (int q = 0; q < world; ++q) s += g[((size_t)q * M + i) * 2 + 1] * expf(g[((size_t)q * M + i) * 2] - m);
+  row_lse[i] = m + logf(s);
+}
+
+int sd_clip_merge_row_stats(const float* gathered, int world, int M, float* row_lse, void* stream) {
+  SD_REQUIRE(gathered && row_lse && world > 0 && M > 0, "sd_clip_merge_row_stats: bad arguments");
+  clip_merge_rows_kernel<<<cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(gathered, world, M, row_lse);
+  return check_launch("clip_merge_rows");
+}
+
 int sd_rownorm2_bf16(const void* x, float* nrm2, int M, int64_t D, void* stream) {
   SD_REQUIRE(D % 8 == 0 && (((uintptr_t)x) & 15) == 0, "sd_rownorm2_bf16: D %% 8 != 0 or unaligned rows");
   cudaStream_t st = (cudaStream_t)stream;

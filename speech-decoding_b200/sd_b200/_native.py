@@ -78,6 +78,7 @@ SIGNATURES = {
     "sd_adam_step": [vp, i32, i32, f32, f32, f32, f32, vp],
     "sd_cast_rows_bf16": [vp, vp, vp, i32, i64, vp],
     "sd_rownorm2_bf16": [vp, vp, i32, i64, vp],
+    "sd_clip_merge_row_stats": [vp, i32, i32, vp, vp],
     "sd_clip_coef_t_bf16": [vp, vp, i32, i32, i32, vp],
     "sd_clip_dots_tc_bf16": [vp, vp, vp, vp, i32, i32, i64, vp],
     "sd_clip_dz_tc_bf16": [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
@@ -92,6 +93,8 @@ SIGNATURES = {
     "sd_memcpy_async": [vp, vp, i64, vp],
     "sd_copy_small": [vp, vp, i64, vp],
     "sd_peer_wait_flags": [vp, i32, i32, vp],
+    "sd_peer_exchange": [vp, i64, vp, i32, i32, i64, i32, vp, vp],
+    "sd_sum_rows": [vp, vp, i32, i32, i32, vp],
 }
 
 _lib = None

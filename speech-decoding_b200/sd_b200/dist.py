@@ -182,6 +182,106 @@ class PeerGather:
             pass
 
 
+class PeerMailbox:
+    """Latency-bound exchanges through peer memory (sd_peer_exchange): every rank owns a mailbox of two parity slots x
+    world rows x CAP bytes, IPC-mapped by its peers; one kernel stores the payload into every peer's mailbox over NVLink,
+    publishes the epoch and waits for the peers'.  Used for the SyncBN statistics, the BatchNorm-backward sums, the CLIP row
+    statistics and the loss partials instead of small NCCL all-reduces."""
+
+    CAP = 64 * 1024
+
+    def __init__(self, group, host_group, device):
+        import ctypes
+        from . import _native as nat
+        self.group, self.device = group, torch.device(device)
+        self.world, self.rank = world_rank(group)
+        self.epoch = 0
+        nbytes = 2 * self.world * self.CAP + 256
+        base = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.call("sd_peer_alloc", ctypes.byref(base), nbytes)
+            self.base = base.value
+            torch.as_tensor(_RawDeviceBuffer(self.base, nbytes), device=self.device).zero_()
+            torch.cuda.synchronize(self.device)
+            hb = ctypes.create_string_buffer(nat.lib().sd_ipc_handle_bytes())
+            nat.call("sd_ipc_get_handle", self.base, hb)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, hb.raw, group=host_group)
+            self.peers = []
+            for r, h in enumerate(everyone):
+                if r == self.rank:
+                    self.peers.append(self.base)
+                else:
+                    out = ctypes.c_void_p()
+                    nat.call("sd_ipc_open_handle", ctypes.create_string_buffer(h, len(h)), ctypes.byref(out))
+                    self.peers.append(out.value)
+            self.peers_dev = torch.tensor(self.peers, dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group=host_group)
+
+    def fits(self, t):
+        return t.is_cuda and t.is_contiguous() and (t.numel() * t.element_size()) % 4 == 0 and t.numel() * t.element_size() <= self.CAP
+
+    def exchange(self, t):
+        """t (contiguous, <= CAP bytes) of every rank -> (world, *t.shape) on every rank, in stream order"""
+        from . import _native as nat
+        self.epoch += 1
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        with torch.cuda.device(self.device):
+            nat.call("sd_peer_exchange", t.data_ptr(), t.numel() * t.element_size(), self.peers_dev.data_ptr(), self.rank, self.world,
+                     self.CAP, self.epoch, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return out
+
+    def all_reduce_sum_(self, t):
+        """t <- sum over ranks of t (fp32 / fp64), summed in rank order: bit-identical on every rank"""
+        from . import _native as nat
+        g = self.exchange(t)
+        with torch.cuda.device(self.device):
+            nat.call("sd_sum_rows", g.data_ptr(), t.data_ptr(), self.world, t.numel(), int(t.dtype == torch.float64),
+                     torch.cuda.current_stream().cuda_stream)
+        return t
+
+    def __del__(self):
+        try:
+            from . import _native as nat
+            for r, p in enumerate(self.peers):
+                if r != self.rank and p:
+                    nat.call("sd_ipc_close_handle", p)
+            nat.call("sd_peer_free", self.base)
+        except Exception:
+            pass
+
+
+_MAILBOX = {}          # id(group) -> PeerMailbox (installed by DataParallel next to the copy-engine gather)
+
+
+def small_all_reduce_sum_(t, group):
+    """In-place SUM all-reduce of a small fp32 / fp64 tensor: through the peer mailbox when there is one, else NCCL / gloo."""
+    mb = _MAILBOX.get(id(group))
+    if mb is not None and t.dtype in (torch.float32, torch.float64) and mb.fits(t):
+        return mb.all_reduce_sum_(t)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def global_row_lse(row_stat, group):
+    """(M,2) per-rank (max_j, sum_j exp(l - max)) over local columns -> (M,) log-sum-exp over the columns of all ranks."""
+    from . import _native as nat
+    world, _ = world_rank(group)
+    if row_stat.is_cuda:
+        mb = _MAILBOX.get(id(group)) if world > 1 else None
+        if world == 1 or (mb is not None and mb.fits(row_stat)):
+            g = row_stat.contiguous() if world == 1 else mb.exchange(row_stat.contiguous())
+            out = torch.empty((row_stat.shape[0],), dtype=torch.float32, device=row_stat.device)
+            with torch.cuda.device(row_stat.device):
+                nat.call("sd_clip_merge_row_stats", g.data_ptr(), world, row_stat.shape[0], out.data_ptr(),
+                         torch.cuda.current_stream().cuda_stream)
+            return out
+    if world > 1:
+        row_stat = merge_row_stats(row_stat, group)
+    return row_stat[:, 0] + torch.log(row_stat[:, 1])
+
+
 _PEER_GATHER = {}      # id(group) -> PeerGather (installed by DataParallel when the copy-engine path is usable)
 
 
@@ -224,9 +324,7 @@ def gather_speech_rows(x2d, group, allow_bf16=True, async_op=False):
 
 
 def all_reduce_sum(t, group):
-    t = t.contiguous()
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    return t
+    return small_all_reduce_sum_(t.contiguous(), group)
 
 
 def merge_row_stats(row_stat, group):
@@ -364,12 +462,14 @@ class DataParallel:
         # speech-row exchange on the copy engines (CUDA IPC peer buffers) instead of an SM-resident NCCL kernel
         if peer_gather is None:
             peer_gather = os.environ.get("SD_B200_DP_GATHER", "peer") != "nccl"
-        self.peer = None
+        self.peer = self.mailbox = None
         dev = next(encoder.parameters()).device
         if peer_gather and dev.type == "cuda" and dist.get_world_size(self.group) > 1:
             try:
                 self.peer = PeerGather(self.group, self.host_group, dev)
                 _PEER_GATHER[id(self.group)] = self.peer
+                self.mailbox = PeerMailbox(self.group, self.host_group, dev)
+                _MAILBOX[id(self.group)] = self.mailbox
             except Exception as e:                                  # pragma: no cover
                 import warnings
                 warnings.warn("sd_b200: copy-engine peer gather unavailable (%s); using the NCCL all-gather" % e)

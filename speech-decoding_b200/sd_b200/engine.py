@@ -314,7 +314,8 @@ class ConvBlockStage(Stage):
             raise RuntimeError("sd_b200: training-mode BatchNorm needs the batch statistics of its producing conv")
         if training and run.bn_group is not None:
             import torch.distributed as dist
-            dist.all_reduce(stats, group=run.bn_group)
+            from . import dist as sd_dist
+            sd_dist.small_all_reduce_sum_(stats, run.bn_group)      # SyncBN: peer-memory exchange (NCCL without a mailbox)
             n = n * dist.get_world_size(run.bn_group)
         ops.bn_finalize(stats, bn.num_features, rup8(bn.num_features), n, bn.weight, bn.bias, bn.running_mean,
                         bn.running_var, bn.num_batches_tracked, momentum, eps, training, ss)

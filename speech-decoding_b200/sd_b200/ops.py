@@ -197,7 +197,8 @@ def bn_gelu_bwd(du, y, ss, red, dgamma, dbeta, C, training, group=None):
     nat.call("sd_bn_gelu_bwd_reduce", _p(du), _p(y), _p(ss), _p(red), rows, Cp, code_of(y), _st())
     if group is not None and training:
         import torch.distributed as dist
-        dist.all_reduce(red, group=group)
+        from . import dist as sd_dist
+        sd_dist.small_all_reduce_sum_(red, group)
         n_stat = rows * dist.get_world_size(group)
         dscale = 1.0 / dist.get_world_size(group)     # red is global already; the grad all-reduce sums once more
     nat.call("sd_bn_bwd_apply", _p(du), _p(y), _p(ss), _p(red), _p(dgamma), _p(dbeta), rows, n_stat, dscale, C, Cp,

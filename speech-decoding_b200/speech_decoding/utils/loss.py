@@ -57,9 +57,7 @@ class _ClipFn(torch.autograd.Function):
                 dots = ops.clip_dots(x, z, tc=tc)
             t = temp.detach() if use_temp else torch.zeros_like(temp)
             logits, row_stat, col_lse = ops.clip_phase1(dots, xn2, zn2, t)
-            if world > 1:
-                row_stat = sd_dist.merge_row_stats(row_stat, group)
-            row_lse = row_stat[:, 0] + torch.log(row_stat[:, 1])
+            row_lse = sd_dist.global_row_lse(row_stat, group)     # one exchange through peer memory + one merge kernel
             scale = 1.0 / M if reduction == "mean" else 1.0
             if x.dtype == torch.bfloat16:      # the bf16 gradient GEMM makes its own transposed bf16 operand
                 coef, cz, partial = ops.clip_phase2(logits, row_lse, col_lse, xn2, zn2, t, scale, rank * Nn)
