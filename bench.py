@@ -308,6 +308,11 @@ def run_ours(a, rank, world, local_rank):
     y_bf16 = a.precision == "bf16" and a.speech_dtype == "bf16"
     if y_bf16:
         Yh = Yh.to(torch.bfloat16)
+    # sensor windows: the bf16 mode rounds X to bf16 in its first kernel, so shipping them in bf16 gives bit-identical
+    # results for half the bytes (tests/test_gpu_parity.py::test_bf16_sensor_input_is_bit_identical)
+    x_bf16 = a.precision == "bf16" and a.sensor_dtype == "bf16"
+    if x_bf16:
+        Xh = Xh.to(torch.bfloat16)
     Xh, Yh = Xh.pin_memory(), Yh.pin_memory()
     X, Y = Xh.to(dev), Yh.to(dev)
 
@@ -491,6 +496,7 @@ def run_ours(a, rank, world, local_rank):
                                    % ("cfg2/cfg3" if CFG["T"] == 360 else "cfg5 long-window" if CFG["T"] == 1200 else "custom-window",
                                       B, CFG["T"], " + grad all-reduce, global-batch CLIP negatives" if world > 1 else ""),
                        "speech_embeddings": "bf16 (rounded once on the host)" if y_bf16 else "fp32",
+                       "sensor_windows": "bf16 (bit-identical results: the bf16 mode rounds X in its first kernel)" if x_bf16 else "fp32",
                        "global_batch": world * B,
                        "precision": a.precision + {"bf16": " activations, fp32 master weights/accumulate",
                                                    "tf32": ": fp32 storage, tcgen05 kind::tf32 convolutions / GEMMs (the reference's cuDNN default)",
@@ -501,8 +507,8 @@ def run_ours(a, rank, world, local_rank):
             "model_tflops_per_s": round(value * gflop / 1e3, 1),
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 3),
                     "h2d_bytes_per_step": int(Xh.numel() * Xh.element_size() + Yh.numel() * Yh.element_size()), "d2h_bytes_per_step": 4,
-                    "includes": "H2D of X (fp32) and Y (%s) from pinned memory (double-buffered on a copy stream), fwd, loss, backward, "
-                                "fused Adam step (sd_adam_step), loss.item()%s" % ("bf16" if y_bf16 else "fp32",
+                    "includes": "H2D of X (%s) and Y (%s) from pinned memory (double-buffered on a copy stream), fwd, loss, backward, "
+                                "fused Adam step (sd_adam_step), loss.item()%s" % ("bf16" if x_bf16 else "fp32", "bf16" if y_bf16 else "fp32",
                                 "; the step is replayed as one CUDA graph (sd_b200.graph.GraphedTrainStep)" if graphed is not None else "")},
             "gpu_launches": launches, "clocks": clk}
     if dp is not None:
@@ -536,6 +542,8 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="e2e leg at 1 GPU: replay the step as one CUDA graph")
     ap.add_argument("--speech-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="storage of the (frozen) speech embeddings Y in the bf16 mode")
+    ap.add_argument("--sensor-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="storage of the sensor windows X in the bf16 mode (bf16 is bit-identical there: X is rounded first thing)")
     ap.add_argument("--window", type=int, default=CFG["T"],
                     help="samples per window: 360 = 3 s (cfg2/cfg3), 1200 = 10 s (BASELINE.json configs[4])")
     ap.add_argument("--no-cpu", action="store_true")

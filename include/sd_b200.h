@@ -64,6 +64,9 @@ int sd_set_sm_limit(int n);
 /* X (B,C,T) fp32 -> (B,T,Cp) dtype, zero padded.  Replaces the implicit layout of
  * einsum("oi,bit->bot") operands, models.py:65. */
 int sd_nct_to_btc(const float* x, void* out, int B, int C, int T, int Cp, int dtype, void* stream);
+/* the same from a bf16 X (sensor windows shipped from the host in bf16: the bf16 mode rounds X to bf16 here anyway, so the
+ * result is bit-identical to shipping fp32 and half the bytes cross PCIe) */
+int sd_nct_to_btc_bf16in(const void* x, void* out, int B, int C, int T, int Cp, int dtype, void* stream);
 /* (B,T,Cp) dtype -> (B,C,T) fp32 (module-facing outputs / gradients of standalone sub-modules) */
 int sd_btc_to_nct(const void* in, float* out, int B, int C, int T, int Cp, int dtype, void* stream);
 

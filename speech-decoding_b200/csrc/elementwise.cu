@@ -8,16 +8,16 @@ namespace sd {
 // ---------------------------------------------------------------------------------------------------
 // (B,C,T) fp32 <-> (B,T,Cp) T : 32x32 shared-memory tile transpose, both sides coalesced
 // ---------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void nct_to_btc_kernel(const float* __restrict__ x, T* __restrict__ out, int C, int Tn, int Cp) {
+template <typename T, typename TIn = float>
+__global__ void nct_to_btc_kernel(const TIn* __restrict__ x, T* __restrict__ out, int C, int Tn, int Cp) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  const float* xb = x + (size_t)b * C * Tn;
+  const TIn* xb = x + (size_t)b * C * Tn;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     int c = c0 + ty + i, t = t0 + tx;
-    tile[ty + i][tx] = (c < C && t < Tn) ? xb[(size_t)c * Tn + t] : 0.f;
+    tile[ty + i][tx] = (c < C && t < Tn) ? to_f<TIn>(xb[(size_t)c * Tn + t]) : 0.f;
   }
   __syncthreads();
   T* ob = out + (size_t)b * Tn * Cp;
@@ -526,6 +526,13 @@ int sd_nct_to_btc(const float* x, void* out, int B, int C, int T_, int Cp, int d
   dim3 grid(cdiv(T_, 32), cdiv(Cp, 32), B), block(32, 8);
   DISPATCH_DTYPE(dtype, nct_to_btc_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(x, (T*)out, C, T_, Cp));
   return check_launch("nct_to_btc");
+}
+
+int sd_nct_to_btc_bf16in(const void* x, void* out, int B, int C, int T_, int Cp, int dtype, void* stream) {
+  SD_REQUIRE(Cp % 8 == 0 && Cp >= C, "sd_nct_to_btc_bf16in: Cp must be a multiple of 8 and >= C");
+  dim3 grid(cdiv(T_, 32), cdiv(Cp, 32), B), block(32, 8);
+  DISPATCH_DTYPE(dtype, nct_to_btc_kernel<T, __nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (T*)out, C, T_, Cp));
+  return check_launch("nct_to_btc_bf16in");
 }
 
 int sd_btc_to_nct(const void* in, float* out, int B, int C, int T_, int Cp, int dtype, void* stream) {

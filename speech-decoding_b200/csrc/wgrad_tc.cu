@@ -13,6 +13,7 @@
 // Split-K over the batch: work item = (n-tile, c-tile, tap, group, split); one item per CTA; the fp32
 // tile is added to dw (PyTorch (N,K,taps) layout, via element strides) with red.global.add.f32.
 // dbias comes from one extra N=16 MMA per k-step against a constant tile of ones.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace sd {
@@ -177,10 +178,27 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(wsn + c * 16 + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
       } else if (n < p.N) {
+        const int cb = c0 + c * 16;
+        float* dst = dwn + cb;
+        if (p.sk == 1 && cb + 16 <= p.K && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+          // contiguous input channels (PyTorch layout of a 1x1 weight): vector reductions, 16 / 8 bytes per L2 atomic
+          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int cc = c0 + c * 16 + i;
-          if (cc < p.K) atomicAdd(dwn + (long long)cc * p.sk, __uint_as_float(r[i]));
+            for (int q = 0; q < 4; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(r[4 * q])),
+                           "f"(__uint_as_float(r[4 * q + 1])), "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3])) : "memory");
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 2 * q), "f"(__uint_as_float(r[2 * q])),
+                           "f"(__uint_as_float(r[2 * q + 1])) : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int cc = cb + i;
+            if (cc < p.K) atomicAdd(dwn + (long long)cc * p.sk, __uint_as_float(r[i]));
+          }
         }
       }
     }
@@ -370,6 +388,49 @@ conv_wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
       }
       if (elect_one_sync()) bulk_wait0();
       __syncwarp();
+    } else if (p.sk == 3 && p.sj == 1) {
+      // PyTorch's (N, K, 3) layout: the three taps of 16 consecutive input channels are 48 consecutive floats of this
+      // thread's row -> vector reductions (red.global.add.v4.f32: one 16-byte L2 atomic per four values) straight into
+      // dw.  The split-K partials never round-trip a workspace and no reduce kernel follows.
+      for (int c = ch0; c < ch1; ++c) {
+        uint32_t r0[16], r1[16], r2[16];
+        tmem_ld16(taddr + c * 16, r0);
+        tmem_ld16(taddr + W3_TAP_COLS + c * 16, r1);
+        tmem_ld16(taddr + 2 * W3_TAP_COLS + c * 16, r2);
+        tmem_ld_wait();
+        const int cb = c0 + c * 16;
+        if (n >= p.N || cb >= p.K) continue;
+        float* dst = dwn + (long long)cb * 3;
+        if (cb + 16 <= p.K) {
+          float v[48];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[3 * i] = __uint_as_float(r0[i]); v[3 * i + 1] = __uint_as_float(r1[i]); v[3 * i + 2] = __uint_as_float(r2[i]);
+          }
+          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                           "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
+          } else if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+#pragma unroll
+            for (int q = 0; q < 24; ++q)
+              asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 2 * q), "f"(v[2 * q]), "f"(v[2 * q + 1]) : "memory");
+          } else {
+#pragma unroll
+            for (int q = 0; q < 48; ++q) atomicAdd(dst + q, v[q]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (cb + i < p.K) {
+              atomicAdd(dst + 3 * i, __uint_as_float(r0[i]));
+              atomicAdd(dst + 3 * i + 1, __uint_as_float(r1[i]));
+              atomicAdd(dst + 3 * i + 2, __uint_as_float(r2[i]));
+            }
+          }
+        }
+      }
     } else {
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
@@ -505,7 +566,11 @@ static int conv_wgrad3_tc(const sd_wgrad_args& a, void* ws, size_t ws_bytes, cud
   }
   size_t bias_off = 0;
   const size_t need = ws_plan(nsplit, 3, p.n_tiles, p.c_tiles, p.block_c, a.dbias != nullptr, &bias_off);
-  const bool use_ws = need > 0 && ws != nullptr && ws_bytes >= need && a.G == 1;
+  // PyTorch-layout weights take the split-K partials by vector reductions straight into dw (see the kernel); the
+  // workspace + reduce-kernel path remains for other layouts (SD_B200_WGRAD_WS=1 forces it: A/B measurements)
+  static const bool force_ws = getenv("SD_B200_WGRAD_WS") != nullptr && getenv("SD_B200_WGRAD_WS")[0] == '1';
+  const bool direct = a.sk == 3 && a.sj == 1 && !force_ws;
+  const bool use_ws = need > 0 && ws != nullptr && ws_bytes >= need && a.G == 1 && !direct;
   p.ws = use_ws ? reinterpret_cast<float*>(ws) : nullptr;
   p.ws_bias = (use_ws && a.dbias) ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + bias_off) : nullptr;
   WsMaps wm;
@@ -576,7 +641,9 @@ int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
   }
   size_t bias_off = 0;
   const size_t need = ws_plan(nsplit, a.taps, p.n_tiles, p.c_tiles, p.block_c, a.dbias != nullptr, &bias_off);
-  const bool use_ws = need > 0 && ws != nullptr && ws_bytes >= need && a.G == 1;
+  static const bool force_ws = getenv("SD_B200_WGRAD_WS") != nullptr && getenv("SD_B200_WGRAD_WS")[0] == '1';
+  const bool direct = a.sk == 1 && !force_ws;      // contiguous channels: vector reductions straight into dw, no reduce kernel
+  const bool use_ws = need > 0 && ws != nullptr && ws_bytes >= need && a.G == 1 && !direct;
   p.ws = use_ws ? reinterpret_cast<float*>(ws) : nullptr;
   p.ws_bias = (use_ws && a.dbias) ? reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + bias_off) : nullptr;
   SD_CUDA(launch_pdl(conv_wgrad_tc_kernel, dim3(base_items * nsplit), dim3(NUM_THREADS), (size_t)smem_bytes, st, 1, tdy, tx, p));

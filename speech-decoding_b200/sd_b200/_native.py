@@ -50,6 +50,7 @@ SIGNATURES = {
     "sd_set_impl": [i32],
     "sd_set_sm_limit": [i32],
     "sd_nct_to_btc": [vp, vp, i32, i32, i32, i32, i32, vp],
+    "sd_nct_to_btc_bf16in": [vp, vp, i32, i32, i32, i32, i32, vp],
     "sd_btc_to_nct": [vp, vp, i32, i32, i32, i32, i32, vp],
     "sd_pack_weight": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "sd_pack_weights": [vp, i32, i32, vp],

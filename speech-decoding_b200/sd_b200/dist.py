@@ -80,6 +80,8 @@ class PeerGather:
         self.base = None             # own receive buffer (device pointer)
         self.peers = None            # device pointers of every rank's receive buffer, mapped into this process
         self.step = 0
+        import os
+        self.NSTREAMS = max(1, int(os.environ.get("SD_B200_DP_STREAMS", self.NSTREAMS)))   # concurrent peer copies
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.NSTREAMS)]
         self.ready = torch.cuda.Event()
         self.consts = torch.arange(1, self.NCONST + 1, dtype=torch.int32, device=self.device)    # flag values to copy from

@@ -527,8 +527,8 @@ class Pipeline:
 
     def run(self, X, subject_ids=None):
         ops.require_cuda(X, "input")
-        if X.dtype != torch.float32:
-            X = X.float()
+        if X.dtype != torch.float32 and not (X.dtype == torch.bfloat16 and not X.requires_grad):
+            X = X.float()            # (a bf16 input is consumed as it is: the layout kernel reads it directly)
         X = X.contiguous()
         self.subject_ids = subject_ids
         params = self.params()

@@ -111,7 +111,7 @@ def nct_to_btc(x, dtype):
     B, C, T = x.shape
     Cp = rup8(C)
     out = torch.empty((B, T, Cp), dtype=dtype, device=x.device)
-    nat.call("sd_nct_to_btc", _p(x), _p(out), B, C, T, Cp, code_of(out), _st())
+    nat.call("sd_nct_to_btc_bf16in" if x.dtype == torch.bfloat16 else "sd_nct_to_btc", _p(x), _p(out), B, C, T, Cp, code_of(out), _st())
     return out
 
 

@@ -302,6 +302,20 @@ def test_clip_accepts_bf16_speech_rows():
     assert G.rel_l2(Z1.grad, Z2.grad) < 2e-2
 
 
+def test_bf16_sensor_input_is_bit_identical():
+    """The bf16 mode rounds the sensor windows to bf16 in its first kernel, so a caller that ships X in bf16 (half the
+    host->device bytes) gets bit-identical latents."""
+    import sd_b200
+    from speech_decoding.models import BrainEncoder
+    sd_b200.set_precision("bf16")
+    args, X, Y, ids = oracle_case(B=8, C=60, T=200, S=5, D1=64, D2=96, Fo=128, K=8, seed=12)
+    enc = BrainEncoder(args).to(DEV).eval()
+    with torch.no_grad():
+        Za = enc(X.to(DEV), ids)
+        Zb = enc(X.to(DEV).to(torch.bfloat16), ids)
+    assert torch.equal(Za, Zb)
+
+
 def test_cfg2_full_size_properties():
     """BASELINE.json configs[1] at full size (B=256, 208 sensors, 360 samples, F=1024), bf16: properties that
     need no oracle -- finite outputs, BN'd activations normalised, CLIP gradient orthogonal to Z rows
