@@ -337,7 +337,8 @@ def run_ours(a, rank, world, local_rank):
         Z = enc(X, ids)
         loss = crit(Y, Z)
         if pipelined:
-            dp.prefetch_targets(Y)          # next step's rows: overlaps backward (copy engines, no SM)
+            # next step's rows: overlap backward (copy engines, no SM), from the point --dp-push-at names
+            dp.prefetch_targets(Y, during_backward=None if a.dp_push_at < 0 else a.dp_push_at)
         for p in opt.param_groups[0]["params"]:
             p.grad = None
         loss.backward()
@@ -537,6 +538,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3", "fp32"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--sync-bn", type=int, default=0)
+    ap.add_argument("--dp-push-at", type=int, default=-1,
+                    help="pipelined gather: start the pushes after the k-th stage from the end of backward (-1: right after the loss forward)")
     ap.add_argument("--dp-pipeline", type=int, default=1,
                     help="N>1: exchange the next step's speech rows during this step's backward (1) or this step's during its forward (0)")
     ap.add_argument("--graph", type=int, default=1, help="e2e leg at 1 GPU: replay the step as one CUDA graph")

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the hot path: layout conversion, weight packing, BatchNorm statistics /
 // apply / backward fused with GELU, GLU, GELU backward.  All operate on the channels-last "BTC"
 // activation layout (rows = B*T, Cp channels contiguous, Cp % 8 == 0) with 8/16-byte vector access.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sd {
@@ -178,7 +179,7 @@ __device__ __forceinline__ F8 unpack8(const Raw8<__nv_bfloat16>& r) {
 
 // MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce over g = du * gelu'(bn(y)) (g is not stored:
 // the apply pass recomputes it, which is cheaper than a 59 MB write + read)
-template <typename T, int MODE>
+template <typename T, int MODE, bool REVERSE = false>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3)
 colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ ss, double* __restrict__ out,
                  int64_t rows, int Cp) {
@@ -200,8 +201,9 @@ colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __rest
     for (int u = 0; u < UNR; ++u) {
       const int64_t rr = r + (int64_t)u * R;
       if (rr < r1) {
-        rv[u] = ldraw8(x + rr * Cp + c);
-        if (MODE == 1) ry_[u] = ldraw8(y + rr * Cp + c);
+        const int64_t rm = REVERSE ? r1 - 1 - rr : rr;     // (sums do not care about the order; the L2 does)
+        rv[u] = ldraw8(x + rm * Cp + c);
+        if (MODE == 1) ry_[u] = ldraw8(y + rm * Cp + c);
       }
     }
 #pragma unroll
@@ -342,7 +344,7 @@ bn_gelu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss, T* __r
 }
 
 // dy = scale * (g - sum_g/n - xhat * sum_gx/n)
-template <typename T>
+template <typename T, bool REVERSE>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ ss,
                     const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -368,20 +370,24 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
     k2.v[i] = training ? -sc.v[i] * is.v[i] * sx : 0.f;
     k3.v[i] = training ? sc.v[i] * (mu.v[i] * is.v[i] * sx - sg) : 0.f;
   }
+  // rows are walked from the END of the tensor: the reduce pass that ran just before walked them front to back, so the
+  // tail is what is still resident in the 126 MB L2 (g and y together are 118 MB at cfg2)
   for (int64_t r = (int64_t)blockIdx.x * UNR * R + ry; r < r1; r += r_stride) {
     Raw8<T> rv[UNR], ry_[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int64_t rr = r + (int64_t)u * R;
       if (rr < r1) {
-        rv[u] = ldraw8(g + rr * Cp + c);
-        ry_[u] = ldraw8(y + rr * Cp + c);
+        const int64_t rm = REVERSE ? r1 - 1 - rr : rr;
+        rv[u] = ldraw8(g + rm * Cp + c);
+        ry_[u] = ldraw8(y + rm * Cp + c);
       }
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int64_t rr = r + (int64_t)u * R;
       if (rr >= r1) break;
+      const int64_t rm = REVERSE ? r1 - 1 - rr : rr;
       F8 v = unpack8(rv[u]);
       const F8 yy = unpack8(ry_[u]);
 #pragma unroll
@@ -389,7 +395,7 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
         const float gg = v.v[i] * gelu_grad_t<T>(fmaf(yy.v[i], sc.v[i], sh.v[i]));
         v.v[i] = training ? fmaf(sc.v[i], gg, fmaf(k2.v[i], yy.v[i], k3.v[i])) : sc.v[i] * gg;
       }
-      st8<T>(g + rr * Cp + c, v);
+      st8<T>(g + rm * Cp + c, v);
     }
   }
 }
@@ -505,6 +511,15 @@ static inline int persistent_grid(int64_t rows, int rows_per_iter, int per_sm) {
   return (int)(groups < g ? (groups > 0 ? groups : 1) : g);
 }
 
+static inline const char* bn_order() {
+  static const char* o = nullptr;
+  if (!o) {
+    const char* e = getenv("SD_B200_BN_ORDER");
+    o = (e && strlen(e) == 2) ? e : "rf";
+  }
+  return o;
+}
+
 static inline int chan_block_rows(int Cp) {
   int r = 256 / (Cp / 8);
   return r < 1 ? 1 : (r > 16 ? 16 : r);
@@ -605,7 +620,13 @@ int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* re
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_gelu_bwd_reduce: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
   const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
-  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1><<<persistent_grid(rows, 4 * block.y, 3), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
+  // Walk order of the two BatchNorm-backward passes (A/B switch SD_B200_BN_ORDER = ff | fr | rf): du was just written front
+  // to back by the data-gradient conv, so its tail is what the L2 still holds
+  if (bn_order()[0] == 'r') {
+    DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1, true><<<persistent_grid(rows, 4 * block.y, 3), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
+  } else {
+    DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1, false><<<persistent_grid(rows, 4 * block.y, 3), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
+  }
   return check_launch("bn_gelu_bwd_reduce");
 }
 
@@ -613,7 +634,12 @@ int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* re
                     int64_t rows, int64_t n_stat, float dparam_scale, int C, int Cp, int training, int dtype, void* stream) {
   SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_bwd_apply: bad Cp");
   dim3 block(Cp / 8, chan_block_rows(Cp));
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<persistent_grid(rows, 2 * block.y, 3), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, dparam_scale, C, Cp, training));
+  const bool fwd_order = bn_order()[1] != 'r';
+  if (fwd_order) {
+    DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T, false><<<persistent_grid(rows, 2 * block.y, 3), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, dparam_scale, C, Cp, training));
+  } else {
+    DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T, true><<<persistent_grid(rows, 2 * block.y, 3), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, dparam_scale, C, Cp, training));
+  }
   return check_launch("bn_bwd_apply");
 }
 

@@ -444,6 +444,7 @@ class DataParallel:
         elif host_group is None:
             self.host_group = self.group
         pipe = encoder.pipeline()
+        self.pipe = pipe
         pipe.reducer = GradReducer(self.group, bucket_bytes)
         pipe.bn_group = self.group if sync_bn else None
         pipe.host_group = self.host_group
@@ -476,13 +477,24 @@ class DataParallel:
                 import warnings
                 warnings.warn("sd_b200: copy-engine peer gather unavailable (%s); using the NCCL all-gather" % e)
 
-    def prefetch_targets(self, Y):
+    def prefetch_targets(self, Y, during_backward=None):
         """Start the all-gather of the speech embeddings for the coming step NOW (they are input data, known
         before the encoder runs), so the transfer over NVLink overlaps the encoder forward instead of sitting
         between the encoder and the loss.  Call right before `encoder(X, ids)`; `loss_fn(Y, Z)` with the same
-        Y then picks the gathered tensor up.  Optional: without it the loss gathers synchronously."""
+        Y then picks the gathered tensor up.  Optional: without it the loss gathers synchronously.
+
+        Pipelined use (a loader that has the NEXT batch ready): call it for the next step's Y between this step's
+        `loss_fn(...)` and `loss.backward()` with during_backward=k: the exchange is then started from inside backward,
+        right after the k-th stage from the end has been enqueued (0 = the final 1x1 convs, whose backward and the CLIP
+        gradient before it are the HBM-bound part of backward; the conv blocks that follow are tensor-bound and lose
+        less to the concurrent copy-engine traffic)."""
         world, _ = world_rank(self.group)
         if world == 1:
+            return
+        if during_backward is not None:
+            pipe = self.pipe
+            idx = len(pipe.stages) - 1 - int(during_backward)
+            pipe.backward_hooks.setdefault(idx, []).append(lambda: self.prefetch_targets(Y))
             return
         from . import ops
         y2 = Y.reshape(Y.shape[0], -1)

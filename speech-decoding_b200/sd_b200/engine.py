@@ -515,6 +515,7 @@ class Pipeline:
         self.out_norm2 = None       # squared row norms of the pipeline output when the last stage produced them
         self._scratch_n = sum(st.scratch for st in stages)
         self.static = None          # graph.StaticInputs while a CUDA-graph step is being captured / replayed
+        self.backward_hooks = {}    # stage index -> [one-shot callables] run right after that stage's backward is enqueued
         self.reducer = None         # dist.GradReducer: per-stage gradient all-reduce (data parallel)
         self.bn_group = None        # process group for SyncBN statistics, or None
         self.host_group = None      # gloo side channel for host-side metadata
@@ -562,6 +563,8 @@ class Pipeline:
             sg = {}
             g = self.stages[i].backward(self, saved[i], g, sg, need_dx or i > 0)
             saved[i] = None          # release activations as we go
+            for hook in self.backward_hooks.pop(i, ()):
+                hook()               # (data parallel: the deferred exchange of the next step's speech rows starts here)
             if self.reducer is not None and self.stages[i].params():
                 # async all-reduce of this stage's contiguous slice overlaps the remaining backward
                 self.reducer.stage_done(self.gpool.flat, *self.gpool.span(self.stages[i].params()))
