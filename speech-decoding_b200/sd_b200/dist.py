@@ -70,7 +70,8 @@ class PeerGather:
     (sd_peer_wait_flags).  Slot reuse is safe with two slots because consecutive steps are separated by a collective
     every rank takes part in (row-statistics exchange in the loss, gradient all-reduce in backward)."""
 
-    NSTREAMS = 4
+    NSTREAMS = 2      # concurrent peer copies: 2 keep the pushes inside backward without slowing the conv grids (measured at N=8:
+                      # 4 streams finish sooner but cost the concurrent conv launches 7 %)
     NCONST = 1024
 
     def __init__(self, group, host_group, device):
