@@ -66,8 +66,9 @@ def _worker(rank, world, port, tmp):
         w.wait()
     assert norms is None and torch.equal(rows, Yg)
     logits, row_stat, col_lse, xn2, zn2 = _phase1(x_all, z_loc, temp)
-    row_stat = sd.merge_row_stats(row_stat, group)
-    row_lse = row_stat[:, 0] + torch.log(row_stat[:, 1])
+    row_lse = sd.global_row_lse(row_stat, group)          # (CPU / gloo: the NCCL-style merge; CUDA: the peer mailbox)
+    merged = sd.merge_row_stats(row_stat, group)
+    assert torch.allclose(row_lse, merged[:, 0] + torch.log(merged[:, 1]))
     coef, cz, partial = _phase2(logits, row_lse, col_lse, xn2, zn2, temp, 1.0 / (world * B), rank * B)
     partial = sd.all_reduce_sum(partial, group)
     dz_loc = coef.T @ x_all - cz[:, None] * z_loc
@@ -81,15 +82,38 @@ def _worker(rank, world, port, tmp):
     assert torch.allclose(dz_loc, Zr.grad[rank * B:(rank + 1) * B], atol=1e-6, rtol=1e-4)
     # ---- per-stage gradient all-reduce on flat slices ----
     flat = torch.arange(20, dtype=torch.float32) * (rank + 1)
-    red = sd.GradReducer(group)
+    want = torch.arange(20, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    red = sd.GradReducer(group, bucket_bytes=0)            # one all-reduce per stage
     red.stage_done(flat, 12, 20)
     red.stage_done(flat, 0, 12)
     red.finish()
-    assert torch.equal(flat, torch.arange(20, dtype=torch.float32) * sum(r + 1 for r in range(world)))
+    assert torch.equal(flat, want) and red.launched == 2
+    # bucketed: adjacent stage slices (stages finish in reverse parameter order) are coalesced until the bucket is full
+    flat = torch.arange(20, dtype=torch.float32) * (rank + 1)
+    red = sd.GradReducer(group, bucket_bytes=10 * 4)
+    red.stage_done(flat, 16, 20)      # 4 elements: bucket open
+    red.stage_done(flat, 9, 16)       # 11 elements >= 10: flushed as [9, 20)
+    red.stage_done(flat, 3, 9)        # 6 elements: open
+    red.stage_done(flat, 0, 3)        # 9 elements: still open -> finish() flushes [0, 9)
+    red.finish()
+    assert torch.equal(flat, want) and red.launched == 2
+    # a non-adjacent slice closes the open bucket first
+    flat = torch.arange(20, dtype=torch.float32) * (rank + 1)
+    red = sd.GradReducer(group, bucket_bytes=1 << 20)
+    red.stage_done(flat, 15, 20)
+    red.stage_done(flat, 0, 5)
+    red.finish()
+    assert torch.equal(flat[15:], want[15:]) and torch.equal(flat[:5], want[:5]) and red.launched == 2
+    assert torch.equal(flat[5:15], torch.arange(5, 15, dtype=torch.float32) * (rank + 1))
+    # small in-place all-reduce: without a peer mailbox (CPU) it is the plain collective
+    t = torch.full((3,), float(rank + 1), dtype=torch.float64)
+    assert torch.equal(sd.small_all_reduce_sum_(t, group), torch.full((3,), 3.0, dtype=torch.float64))
     # ---- subject presence agreed on the host ----
     ids = np.array([0, 3, 3]) if rank == 0 else np.array([5, 5, 1])
     present = np.unique(np.concatenate(sd.gather_host_ints(ids, group)))
     assert present.tolist() == [0, 1, 3, 5]
+    collect = sd.gather_host_ints_async(ids, group)        # started in the forward, collected in backward
+    assert np.unique(np.concatenate(collect())).tolist() == [0, 1, 3, 5]
     open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
     dist.destroy_process_group()
 

@@ -95,3 +95,53 @@ def test_two_gpu_data_parallel_matches_global_batch_oracle(tmp_path, precision):
     from tests import parity_log as PL
     for k, v in json.load(open(tmp_path / "measured.json")).items():
         PL.record(k, v, 1e-4 if precision == "fp32" else (1e-1 if k == "grad_worst" else 5e-2))
+
+
+def _peer_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    host = dist.new_group(backend="gloo")
+    import sd_b200
+    from sd_b200 import dist as sd
+    sd_b200.set_precision("bf16")
+    # ---- one-kernel all-gather through peer memory: many epochs back to back, fp32 / fp64 payloads of varying size ----
+    mb = sd.PeerMailbox(dist.group.WORLD, host, dev)
+    for it in range(40):
+        n = [2, 640, 4096, 1][it % 4]
+        dt = torch.float64 if it % 3 == 0 else torch.float32
+        t = (torch.arange(n, device=dev, dtype=dt) + 1000.0 * rank + it)
+        g = mb.exchange(t)
+        for q in range(world):
+            assert torch.equal(g[q], torch.arange(n, device=dev, dtype=dt) + 1000.0 * q + it), (it, q)
+        s = mb.all_reduce_sum_(t.clone())
+        assert torch.equal(s, sum(torch.arange(n, device=dev, dtype=dt) + 1000.0 * q + it for q in range(world)))
+    # ---- copy-engine gather of bf16 rows + norms with the flag fence: several steps, both parity slots ----
+    pg = sd.PeerGather(dist.group.WORLD, host, dev)
+    rows, D = 24, 4096
+    for it in range(6):
+        xb = (torch.randn(rows, D, device=dev, generator=torch.Generator(device=dev).manual_seed(100 * it + rank))).to(torch.bfloat16)
+        n2 = (xb.float() ** 2).sum(1)
+        allrows, allnorms, works = pg.gather(xb, n2)
+        for w in works:
+            w.wait()
+        for q in range(world):
+            ref = torch.randn(rows, D, device=dev, generator=torch.Generator(device=dev).manual_seed(100 * it + q)).to(torch.bfloat16)
+            assert torch.equal(allrows[q * rows:(q + 1) * rows], ref), (it, q)
+            assert torch.equal(allnorms[q * rows:(q + 1) * rows], (ref.float() ** 2).sum(1)), (it, q)
+        # the step's closing collective (gradient all-reduce in training) is what makes two slots sufficient
+        dist.all_reduce(torch.zeros(1, device=dev))
+    torch.cuda.synchronize()
+    open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_peer_memory_exchange_and_copy_engine_gather(tmp_path):
+    """The two peer-memory primitives of the data-parallel path (sd_peer_exchange mailbox, copy-engine PeerGather with its
+    flag fence) against their definitions, over many epochs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_peer_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
