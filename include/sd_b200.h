@@ -125,6 +125,11 @@ typedef struct {
                           (tensor-core path, SD_ACT_GELU with a BTC output) */
   const void* in_lo;   /* SD_TF32 only, or NULL: low planes of `in` / `w` (same shapes) from sd_tf32_split; both or   */
   const void* w_lo;    /* neither.  Given: 3xTF32 (in, w must then be the HIGH planes).                                */
+  const void* bnr_y;   /* BatchNorm backward fused into a data-gradient conv (bf16 tensor-core path), or NULL.  The conv result */
+  const float* bnr_ss; /* is du, the gradient w.r.t. u = gelu(bn(y)) (models.py:158,161).  With bnr_y = that y (B,T,Np) and  */
+                       /* bnr_ss = (2,Np) the BatchNorm's scale / shift, the epilogue stores g = du * gelu'(scale*y + shift)   */
+                       /* to `out` instead of du and adds sum g, sum g*y over (b,t) to `stats` (2,Np) -- the reduce pass of   */
+                       /* sd_bn_gelu_bwd_reduce; sd_bn_bwd_apply then runs with g_ready = 1.  Needs act NONE, BTC out, no bias. */
 } sd_conv_args;
 int sd_conv_fwd(const sd_conv_args* a, void* stream);
 
@@ -180,6 +185,10 @@ int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* re
 int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* red, float* dgamma,
                     float* dbeta, int64_t rows, int64_t n_stat, float dparam_scale, int C, int Cp, int training,
                     int dtype, void* stream);
+/* the same when g_dy already holds g (written by a conv with bnr_y): no GELU derivative is recomputed */
+int sd_bn_bwd_apply_g(void* g_dy, const void* y, const float* ss, const double* red, float* dgamma,
+                      float* dbeta, int64_t rows, int64_t n_stat, float dparam_scale, int C, int Cp, int training,
+                      int dtype, void* stream);
 
 /* ---- GLU (models.py:164) and GELU backward ------------------------------------------------------- */
 int sd_glu_fwd(const void* y2, void* out, int64_t rows, int D2, int Np, int Op, int dtype, void* stream);

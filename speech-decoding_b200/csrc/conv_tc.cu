@@ -49,6 +49,8 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 struct FwdParams {
   const float* bias;
   const float* affine;   // (2, Np) per-channel scale, shift before the activation (folded eval-mode BatchNorm) or null
+  const float* bnr_ss;   // BatchNorm-backward fusion (see the epilogue): (2, Np) scale, shift of the BatchNorm whose input is bnr_y
+  int bnr;
   const __nv_bfloat16* res;
   __nv_bfloat16* out_btc;
   float* out_nct;
@@ -66,6 +68,7 @@ struct FwdParams {
 // tensor maps of the epilogue tensors, one per column-half of the tile (the halves may differ in width)
 struct EpiMaps {
   CUtensorMap out[2], pre[2], res[2], preb[2];   // preb: gate half of the GLU pre-activation
+  CUtensorMap yin[2];                            // BatchNorm-backward fusion: the forward pre-BN tensor y
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -183,6 +186,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   auto tempty_bar = [&](int a) { return bar_base + 8u * (NB + 2 + a); };
   auto res_bar = [&](int w) { return bar_base + 8u * (NB + 4 + w); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (NB + 4 + NUM_EPI_WARPS);
+  auto y_bar = [&](int w) { return bar_base + 8u * (NB + 4 + NUM_EPI_WARPS + 1 + w); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool glu = p.act == SD_ACT_GLU;
@@ -216,7 +220,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
     }
-    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(res_bar(w), 1); mbar_init(y_bar(w), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -241,11 +245,12 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     if (p.stats)
       for (int i = threadIdx.x; i < 8 * p.cols_alloc; i += NUM_THREADS) s_stats[i] = 0.f;   // [quadrant][sum, sumsq][col]
-    if (p.affine) {   // scale (1 beyond Np) and shift (0 beyond Np)
+    if (p.affine || p.bnr) {   // scale (1 beyond Np) and shift (0 beyond Np)
+      const float* src = p.affine ? p.affine : p.bnr_ss;
       float* s_aff = reinterpret_cast<float*>(smem_gen + p.off_affine);
       for (int i = threadIdx.x; i < p.cols_alloc; i += NUM_THREADS) {
-        s_aff[i] = i < p.Np ? p.affine[i] : 1.f;
-        s_aff[p.cols_alloc + i] = i < p.Np ? p.affine[p.Np + i] : 0.f;
+        s_aff[i] = i < p.Np ? src[i] : 1.f;
+        s_aff[p.cols_alloc + i] = i < p.Np ? src[p.Np + i] : 0.f;
       }
     }
   }
@@ -432,7 +437,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const CUtensorMap* m_pre = &em.pre[hsel];
     const CUtensorMap* m_res = &em.res[hsel];
     const CUtensorMap* m_preb = &em.preb[hsel];
-    uint32_t res_ph = 0;
+    const CUtensorMap* m_yin = &em.yin[hsel];
+    uint32_t res_ph = 0, y_ph = 0;
     TL(long long tl_t0 = clock64(), tl_rd = 0, tl_tf = 0, tl_rs = 0, tl_ch = 0, tl_st = 0, tl_q, tl_r;)
 
     // fetch this warp's residual tile of tile `tl` (non-GLU only)
@@ -453,6 +459,26 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       __syncwarp();
     };
     if (p.res && tile_begin < tile_end) fetch_residual(tile_begin);
+    // BatchNorm-backward fusion: this warp's tile of the forward pre-BN tensor y, fetched INTO THE OUTPUT STAGING TILE (the
+    // epilogue reads a y chunk, computes g and writes g back to the same place, so no extra shared memory is needed);
+    // issued as soon as the previous tile's tensor store has finished reading the staging tile, i.e. early in this
+    // tile's mainloop
+    auto fetch_y = [&](const int tl) {
+      const int m_tile = ws ? tl : tl / p.n_tiles, n_idx = ws ? n_fixed : tl % p.n_tiles;
+      const int m_idx = PAIR ? 2 * m_tile + rank : m_tile;
+      const int b = m_idx / p.m_tiles_per_sample;
+      const int t_w = (m_idx % p.m_tiles_per_sample) * BLOCK_M + quad * 32;
+      const int c0 = n_idx * p.block_n + seg_col;
+      if (elect_one_sync()) {
+        if (seg_cols > 0 && t_w < p.T && b < p.B && c0 < p.Np) {
+          mbar_arrive_expect_tx(y_bar(ew), box_bytes);
+          tma_load_3d(stg0, m_yin, y_bar(ew), c0, t_w, b);
+        } else {
+          mbar_arrive(y_bar(ew));
+        }
+      }
+      __syncwarp();
+    };
 
     int it_tile = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it_tile) {
@@ -473,6 +499,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       TL(tl_q = clock64();)
       if (elect_one_sync()) bulk_wait_read0();
       __syncwarp();
+      if (p.bnr) fetch_y(tile);
       TL(tl_r = clock64(); tl_rd += tl_r - tl_q; tl_q = tl_r;)
       mbar_wait_relaxed(tfull_bar(acc), acc_ph);
       tc_fence_after();
@@ -480,6 +507,10 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (p.res) {
         mbar_wait(res_bar(ew), res_ph);
         res_ph ^= 1;
+      }
+      if (p.bnr) {
+        mbar_wait(y_bar(ew), y_ph);
+        y_ph ^= 1;
       }
       TL(tl_r = clock64(); tl_rs += tl_r - tl_q; tl_q = tl_r;)
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * MAX_BLOCK_N;
@@ -499,6 +530,38 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           lds16_f32_add(s_bias + nb * 4, v);
           if (p.res && live) lds16_bf16_add(myr + so, v);
           if (p.affine) lds16_f32_affine(s_aff + nb * 4, s_aff + (p.cols_alloc + nb) * 4, v);
+          if (p.bnr) {
+            // v = du (gradient w.r.t. u = gelu(bn(y))) for this thread's row and 16 channels.  g = du * gelu'(scale*y +
+            // shift), rounded to bf16 as it will be stored; the BatchNorm-backward sums  sum g, sum g*y  over the rows are
+            // taken here (the stand-alone reduce pass over du and y disappears), g replaces y in the staging tile
+            float yv[16], gy[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              yv[i] = 0.f;
+              if (!valid) v[i] = 0.f;       // rows beyond T: their taps reach valid rows, but they are not part of the tensor
+            }
+            if (live) lds16_bf16_add(my0 + so, yv);
+            float xh[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xh[i] = yv[i];
+            lds16_f32_affine(s_aff + nb * 4, s_aff + (p.cols_alloc + nb) * 4, xh);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] = bf16_round(v[i] * gelu_grad_fast(xh[i]));
+              gy[i] = v[i] * yv[i];
+            }
+            sts16_bf16(my0 + so, v);
+            float gs[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gs[i] = v[i];
+            const float cs = warp_colsum16(gs, lane), cq = warp_colsum16(gy, lane);
+            if ((lane & 1) == 0 && live) {       // this (quadrant, column) accumulator belongs to this warp: plain read-modify-write
+              const int col = nb + col_of_lane(lane);
+              s_stats[quad * 2 * p.cols_alloc + col] += cs;
+              s_stats[(quad * 2 + 1) * p.cols_alloc + col] += cq;
+            }
+            continue;
+          }
           if (p.act == SD_ACT_GELU) {
             if (p.preact) sts16_bf16(my0 + so, v);
 #pragma unroll
@@ -531,7 +594,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         __syncwarp();
         if (p.res && tile + tile_step < tile_end) fetch_residual(tile + tile_step);   // a whole tile ahead
         TL(tl_r = clock64(); tl_ch += tl_r - tl_q; tl_q = tl_r;)
-        if (p.stats && live) {
+        if (p.stats && !p.bnr && live) {
           // BatchNorm batch statistics of the values exactly as stored (bf16): column sums over this warp's
           // staged tile -- lane = column pair, conflict-free 4-byte reads down the rows
           const int rows_valid = min(32, p.T - t_w);
@@ -738,11 +801,14 @@ void set_conv_pair(int on, bool ws) {   // on: 0 never, 1 where it pays (default
 bool conv_fwd_tc_supported(const sd_conv_args& a) {
   if (a.dtype != SD_BF16) return false;
   if (a.act == SD_ACT_GLU && ((a.N / 2) % 8 != 0 || a.out_mode != SD_OUT_BTC || a.N % 2)) return false;
-  if (a.stats && (a.act != SD_ACT_NONE || a.out_mode != SD_OUT_BTC)) return false;
+  if (a.stats && (a.act != SD_ACT_NONE || a.out_mode != SD_OUT_BTC)) return false;   // (forward BN statistics, or with bnr_y the BN-backward sums)
   if (a.rownorm2 && a.out_mode != SD_OUT_NCT_F32) return false;
   if (a.res && ((a.act != SD_ACT_NONE && a.act != SD_ACT_GELU) || a.out_mode != SD_OUT_BTC)) return false;
   if (a.affine && (a.act != SD_ACT_GELU || a.out_mode != SD_OUT_BTC || a.preact || a.stats)) return false;
   if (a.out_mode == SD_OUT_NCT_F32 && a.act != SD_ACT_GELU) return false;
+  if (a.bnr_y && (a.act != SD_ACT_NONE || a.out_mode != SD_OUT_BTC || a.preact || a.affine || a.bias || !a.stats || !a.bnr_ss ||
+                  ((uintptr_t)a.bnr_y & 15)))
+    return false;
   if (((uintptr_t)a.in & 15) || ((uintptr_t)a.w & 15) || ((uintptr_t)a.out & 15) || ((uintptr_t)a.res & 15) ||
       ((uintptr_t)a.preact & 15))
     return false;
@@ -756,6 +822,8 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   p.bias = a.bias;
   p.affine = a.affine;
+  p.bnr = a.bnr_y != nullptr;
+  p.bnr_ss = a.bnr_ss;
   p.res = reinterpret_cast<const __nv_bfloat16*>(a.res);
   p.out_btc = reinterpret_cast<__nv_bfloat16*>(a.out);
   p.out_nct = reinterpret_cast<float*>(a.out);
@@ -808,7 +876,7 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
     const int stg1_bytes = need_stg1 ? BLOCK_M * (glu ? bn / 2 : bn) * 2 : 0;
     const int stgr_bytes = a.res ? BLOCK_M * bn * 2 : 0;
     const int stats_bytes = a.stats ? 8 * p.cols_alloc * 4 : 0;   // per TMEM quadrant: sums and sums of squares
-    const int affine_bytes = a.affine ? 2 * p.cols_alloc * 4 : 0;
+    const int affine_bytes = (a.affine || a.bnr_y) ? 2 * p.cols_alloc * 4 : 0;
     const int tail = stg_bytes + stg1_bytes + stgr_bytes + (glu ? 2 : 1) * p.cols_alloc * 4 + stats_bytes + affine_bytes + 16 + 512;
     const int ring = SMEM_LIMIT - 1024 - tail;
     int sa, sw, w_region;
@@ -870,7 +938,7 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
   const int widths[2] = {w0, w1};
   for (int h = 0; h < 2; ++h) {
     const uint32_t w = (uint32_t)widths[h];
-    if (w == 0) { em.out[h] = em.out[0]; em.pre[h] = em.pre[0]; em.res[h] = em.res[0]; em.preb[h] = em.preb[0]; continue; }
+    if (w == 0) { em.out[h] = em.out[0]; em.pre[h] = em.pre[0]; em.res[h] = em.res[0]; em.preb[h] = em.preb[0]; em.yin[h] = em.yin[0]; continue; }
     const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const CUtensorMapSwizzle NS = CU_TENSOR_MAP_SWIZZLE_NONE;
     if (a.out_mode == SD_OUT_BTC) {
@@ -896,6 +964,11 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
       if (make_tmap_3d(&em.res[h], BF, a.res, (uint64_t)a.Np, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, w, 32, 1, NS)) return 1;
     } else {
       em.res[h] = ta_dummy();
+    }
+    if (a.bnr_y) {
+      if (make_tmap_3d(&em.yin[h], BF, a.bnr_y, (uint64_t)a.Np, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.Np * 2, (uint64_t)a.T * a.Np * 2, w, 32, 1, NS)) return 1;
+    } else {
+      em.yin[h] = ta_dummy();
     }
   }
 

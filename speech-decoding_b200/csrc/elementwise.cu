@@ -344,8 +344,8 @@ bn_gelu_fwd_kernel(const T* __restrict__ y, const float* __restrict__ ss, T* __r
 }
 
 // dy = scale * (g - sum_g/n - xhat * sum_gx/n)
-template <typename T, bool REVERSE>
-__global__ void __launch_bounds__(256, 3)
+template <typename T, bool REVERSE, bool G_READY = false>
+__global__ void __launch_bounds__(256, G_READY ? 4 : 3)
 bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __restrict__ ss,
                     const double* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     int64_t rows, int64_t n_stat, float dscale, int C, int Cp, int training) {
@@ -392,7 +392,7 @@ bn_bwd_apply_kernel(T* __restrict__ g, const T* __restrict__ y, const float* __r
       const F8 yy = unpack8(ry_[u]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float gg = v.v[i] * gelu_grad_t<T>(fmaf(yy.v[i], sc.v[i], sh.v[i]));
+        const float gg = G_READY ? v.v[i] : v.v[i] * gelu_grad_t<T>(fmaf(yy.v[i], sc.v[i], sh.v[i]));
         v.v[i] = training ? fmaf(sc.v[i], gg, fmaf(k2.v[i], yy.v[i], k3.v[i])) : sc.v[i] * gg;
       }
       st8<T>(g + rm * Cp + c, v);
@@ -641,6 +641,14 @@ int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* re
     DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T, true><<<persistent_grid(rows, 2 * block.y, 3), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, dparam_scale, C, Cp, training));
   }
   return check_launch("bn_bwd_apply");
+}
+
+int sd_bn_bwd_apply_g(void* g_dy, const void* y, const float* ss, const double* red, float* dgamma, float* dbeta,
+                      int64_t rows, int64_t n_stat, float dparam_scale, int C, int Cp, int training, int dtype, void* stream) {
+  SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_bwd_apply_g: bad Cp");
+  dim3 block(Cp / 8, chan_block_rows(Cp));
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T, false, true><<<persistent_grid(rows, 2 * block.y, 4), block, 0, (cudaStream_t)stream>>>((T*)g_dy, (const T*)y, ss, red, dgamma, dbeta, rows, n_stat, dparam_scale, C, Cp, training));
+  return check_launch("bn_bwd_apply_g");
 }
 
 int sd_glu_fwd(const void* y2, void* out, int64_t rows, int D2, int Np, int Op, int dtype, void* stream) {

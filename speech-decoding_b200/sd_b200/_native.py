@@ -21,7 +21,8 @@ class ConvArgs(C.Structure):
                 ("preact", vp), ("stats", vp), ("rownorm2", vp),
                 ("B", i32), ("T", i32), ("K", i32), ("Kp", i32), ("N", i32), ("Np", i32),
                 ("taps", i32), ("dil", i32), ("G", i32),
-                ("act", i32), ("out_mode", i32), ("dtype", i32), ("affine", vp), ("in_lo", vp), ("w_lo", vp)]
+                ("act", i32), ("out_mode", i32), ("dtype", i32), ("affine", vp), ("in_lo", vp), ("w_lo", vp),
+                ("bnr_y", vp), ("bnr_ss", vp)]
 
 
 class AdamEntry(C.Structure):
@@ -64,6 +65,7 @@ SIGNATURES = {
     "sd_bn_gelu_fwd": [vp, vp, vp, i64, i32, i32, vp],
     "sd_bn_gelu_bwd_reduce": [vp, vp, vp, vp, i64, i32, i32, vp],
     "sd_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, i64, i64, f32, i32, i32, i32, i32, vp],
+    "sd_bn_bwd_apply_g": [vp, vp, vp, vp, vp, vp, i64, i64, f32, i32, i32, i32, i32, vp],
     "sd_glu_fwd": [vp, vp, i64, i32, i32, i32, i32, vp],
     "sd_glu_bwd": [vp, vp, vp, i64, i32, i32, i32, i32, vp],
     "sd_gelu_bwd": [vp, vp, i64, i32, i32, vp],

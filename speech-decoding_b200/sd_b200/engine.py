@@ -385,12 +385,16 @@ class ConvBlockStage(Stage):
         ops.glu_bwd(dout, sv["y2"], dy2, D2)
         dw2, db2 = zl(m.conv2.weight), zl(m.conv2.bias)
         ops.conv_wgrad(dy2, sv["u1"], dw2, K=D2, N=2 * D2, taps=3, dil=d2, dbias=db2)
+        # The data-gradient convs that feed a BatchNorm backward carry its reduce pass in their epilogue (bf16 tensor-core
+        # path): they store g = du * gelu'(bn(y)) and accumulate sum g, sum g*y, so only the apply pass remains
+        fuse = ops.bn_bwd_fusable(sv["y1"])
         du1 = torch.empty_like(sv["u1"])
-        ops.conv_fwd(dy2, run.pack.wd(self.key + ".c2"), K=2 * D2, N=D2, taps=3, dil=d2, out=du1)
+        ops.conv_fwd(dy2, run.pack.wd(self.key + ".c2"), K=2 * D2, N=D2, taps=3, dil=d2, out=du1,
+                     **(dict(bnr_y=sv["y1"], bnr_ss=ss[1], stats=red[1]) if fuse else {}))
         del dy2
         # bn1 + gelu
         dg1, dbt1 = zl(m.batchnorm1.weight), zl(m.batchnorm1.bias)
-        ops.bn_gelu_bwd(du1, sv["y1"], ss[1], red[1], dg1, dbt1, D2, train, run.bn_group)
+        ops.bn_gelu_bwd(du1, sv["y1"], ss[1], red[1], dg1, dbt1, D2, train, run.bn_group, g_ready=fuse)
         dy1 = du1
         dw1, db1 = zl(m.conv1.weight), zl(m.conv1.bias)
         # bias of a conv that feeds a training-mode BatchNorm: its gradient sum_rows(dy) is identically zero (BN
@@ -398,10 +402,11 @@ class ConvBlockStage(Stage):
         # the kernel skips its bias MMAs.  Eval-mode BN (running statistics) keeps the real bias gradient.
         ops.conv_wgrad(dy1, sv["u0"], dw1, K=D2, N=D2, taps=3, dil=d1, dbias=None if train else db1)
         du0 = torch.empty_like(dy1)
-        ops.conv_fwd(dy1, run.pack.wd(self.key + ".c1"), K=D2, N=D2, taps=3, dil=d1, res=dy1, out=du0)
+        ops.conv_fwd(dy1, run.pack.wd(self.key + ".c1"), K=D2, N=D2, taps=3, dil=d1, res=dy1, out=du0,
+                     **(dict(bnr_y=sv["y0"], bnr_ss=ss[0], stats=red[0]) if fuse else {}))
         # bn0 + gelu
         dg0, dbt0 = zl(m.batchnorm0.weight), zl(m.batchnorm0.bias)
-        ops.bn_gelu_bwd(du0, sv["y0"], ss[0], red[0], dg0, dbt0, D2, train, run.bn_group)
+        ops.bn_gelu_bwd(du0, sv["y0"], ss[0], red[0], dg0, dbt0, D2, train, run.bn_group, g_ready=fuse)
         dy0 = du0
         dw0, db0 = zl(m.conv0.weight), zl(m.conv0.bias)
         ops.conv_wgrad(dy0, sv["x"], dw0, K=Cin, N=D2, taps=3, dil=d0, dbias=None if train else db0)

@@ -124,7 +124,7 @@ def btc_to_nct(a, C):
 
 # ---- conv ----------------------------------------------------------------------------------------
 def conv_fwd(inp, w, *, K, N, taps=1, dil=1, bias=None, res=None, widx=None, G=1, out=None, preact=None,
-             stats=None, rownorm2=None, act=nat.ACT_NONE, out_mode=nat.OUT_BTC, affine=None):
+             stats=None, rownorm2=None, act=nat.ACT_NONE, out_mode=nat.OUT_BTC, affine=None, bnr_y=None, bnr_ss=None):
     B, T, Kp = inp.shape
     Np = rup8(N)
     code, in_lo, w_lo = code_of(inp), None, None
@@ -135,7 +135,7 @@ def conv_fwd(inp, w, *, K, N, taps=1, dil=1, bias=None, res=None, widx=None, G=1
             inp, in_lo = tf32_split(inp)
             w, w_lo = tf32_split(w)
     a = nat.ConvArgs(_p(inp), _p(w), _p(bias), _p(res), _p(widx), _p(out), _p(preact), _p(stats), _p(rownorm2),
-                     B, T, K, Kp, N, Np, taps, dil, G, act, out_mode, code, _p(affine), _p(in_lo), _p(w_lo))
+                     B, T, K, Kp, N, Np, taps, dil, G, act, out_mode, code, _p(affine), _p(in_lo), _p(w_lo), _p(bnr_y), _p(bnr_ss))
     nat.call("sd_conv_fwd", a, _st())
     return out
 
@@ -189,20 +189,30 @@ def bn_gelu_fwd(y, ss, u):
     nat.call("sd_bn_gelu_fwd", _p(y), _p(ss), _p(u), rows, y.shape[2], code_of(y), _st())
 
 
-def bn_gelu_bwd(du, y, ss, red, dgamma, dbeta, C, training, group=None):
+def bn_bwd_fusable(y):
+    """can the BatchNorm-backward reduce ride in the epilogue of the conv that produces du?  (bf16 tensor-core path)"""
+    return y.dtype == torch.bfloat16 and get_impl() != "simt" and _BNR_FUSE
+
+
+_BNR_FUSE = os.environ.get("SD_B200_BNR_FUSE", "1") != "0"
+
+
+def bn_gelu_bwd(du, y, ss, red, dgamma, dbeta, C, training, group=None, g_ready=False):
     """in place: du -> dy (gradient w.r.t. the pre-BN tensor y).  With `group`
-    (SyncBN) the two per-channel sums are all-reduced between the passes."""
+    (SyncBN) the two per-channel sums are all-reduced between the passes.
+    g_ready: `du` already holds g = du * gelu'(bn(y)) and `red` its sums (written by the producing conv, bnr_y)."""
     rows, Cp = y.shape[0] * y.shape[1], y.shape[2]
     n_stat, dscale = rows, 1.0
-    nat.call("sd_bn_gelu_bwd_reduce", _p(du), _p(y), _p(ss), _p(red), rows, Cp, code_of(y), _st())
+    if not g_ready:
+        nat.call("sd_bn_gelu_bwd_reduce", _p(du), _p(y), _p(ss), _p(red), rows, Cp, code_of(y), _st())
     if group is not None and training:
         import torch.distributed as dist
         from . import dist as sd_dist
         sd_dist.small_all_reduce_sum_(red, group)
         n_stat = rows * dist.get_world_size(group)
         dscale = 1.0 / dist.get_world_size(group)     # red is global already; the grad all-reduce sums once more
-    nat.call("sd_bn_bwd_apply", _p(du), _p(y), _p(ss), _p(red), _p(dgamma), _p(dbeta), rows, n_stat, dscale, C, Cp,
-             int(training), code_of(y), _st())
+    nat.call("sd_bn_bwd_apply_g" if g_ready else "sd_bn_bwd_apply", _p(du), _p(y), _p(ss), _p(red), _p(dgamma), _p(dbeta), rows,
+             n_stat, dscale, C, Cp, int(training), code_of(y), _st())
 
 
 def glu_bwd(dout, y2, dy2, D2):

@@ -427,3 +427,64 @@ def test_conv_cta_pair_matches_single_cta(B, T, K, N, taps, dil, mode):
         assert rel(b["out"], F.gelu(y, approximate="tanh")) < TOL[dtype]
     else:
         assert rel(ops.btc_to_nct(b["out"], N), F.gelu(y, approximate="tanh")) < TOL[dtype]
+
+
+@pytest.mark.parametrize("B,T,K,N,dil,with_res", [(3, 50, 24, 40, 1, False), (100, 360, 320, 320, 4, True), (2, 360, 640, 320, 2, False),
+                                                  (5, 200, 320, 320, 16, True)])
+def test_conv_dgrad_with_fused_batchnorm_backward_reduce(B, T, K, N, dil, with_res):
+    """sd_conv_args.bnr_y: the data-gradient conv stores g = du * gelu'(scale*y + shift) and accumulates the BatchNorm-backward
+    sums in its epilogue.  Against the unfused sequence (conv -> sd_bn_gelu_bwd_reduce -> sd_bn_bwd_apply) and the fp32 math."""
+    ops, nat = _ops()
+    import sd_b200
+    sd_b200.set_precision("bf16")
+    dt = torch.bfloat16
+    torch.manual_seed(7)
+    x = torch.randn(B, K, T, device=DEV)
+    w = torch.randn(N, K, 3, device=DEV) / (3 * K) ** 0.5
+    y = torch.randn(B, N, T, device=DEV) * 1.5 + 0.3
+    res = torch.randn(B, N, T, device=DEV) if with_res else None
+    gamma, beta = torch.rand(N, device=DEV) + 0.5, torch.randn(N, device=DEV) * 0.2
+    xt, yt = ops.nct_to_btc(x, dt), ops.nct_to_btc(y, dt)
+    rt = ops.nct_to_btc(res, dt) if with_res else None
+    wf, _ = pack(w, dt)
+    Np = ops.rup8(N)
+    # BatchNorm scale / shift / mean / invstd of y as the forward would have left them
+    yf = yt.float()[:, :, :N]
+    mean, var = yf.mean(dim=(0, 1)), yf.var(dim=(0, 1), unbiased=False)
+    invstd = (var + 1e-5).rsqrt()
+    ss = torch.zeros((4, Np), device=DEV)
+    ss[0, :N], ss[1, :N], ss[2, :N], ss[3, :N] = gamma * invstd, beta - mean * gamma * invstd, mean, invstd
+    rows = B * T
+
+    def run(fused):
+        out = torch.empty((B, T, Np), dtype=dt, device=DEV)
+        red = torch.zeros((2, Np), dtype=torch.float64, device=DEV)
+        dg, db = torch.zeros(N, device=DEV), torch.zeros(N, device=DEV)
+        if fused:
+            ops.conv_fwd(xt, wf, K=K, N=N, taps=3, dil=dil, res=rt, out=out, bnr_y=yt, bnr_ss=ss, stats=red)
+        else:
+            ops.conv_fwd(xt, wf, K=K, N=N, taps=3, dil=dil, res=rt, out=out)
+        ops.bn_gelu_bwd(out, yt, ss, red, dg, db, N, True, None, g_ready=fused)
+        return out.float()[:, :, :N], red[:, :N].clone(), dg, db
+
+    dy_f, red_f, dg_f, db_f = run(True)
+    dy_u, red_u, dg_u, db_u = run(False)
+    # fp32 statement of the whole thing (tanh-form GELU derivative is within bf16 noise of the erf form)
+    du = F.conv1d(xt.float()[:, :, :K].transpose(1, 2), w.to(dt).float(), None, padding=dil, dilation=dil)
+    if with_res:
+        du = du + rt.float()[:, :, :N].transpose(1, 2)
+    yn = yf.transpose(1, 2)
+    pre = (yn * ss[0, :N, None] + ss[1, :N, None]).requires_grad_(True)
+    F.gelu(pre).backward(du)
+    g = pre.grad
+    xhat = (yn - mean[:, None]) * invstd[:, None]
+    sg, sgx = g.sum(dim=(0, 2)), (g * xhat).sum(dim=(0, 2))
+    dy_ref = (gamma * invstd)[:, None] * (g - sg[:, None] / rows - xhat * sgx[:, None] / rows)
+
+    def nerr(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm())
+    assert nerr(red_f[0], red_u[0]) < 5e-3 and nerr(red_f[1], red_u[1]) < 5e-3        # fused sums see the unrounded du
+    assert nerr(dy_f, dy_u) < 1e-2
+    assert nerr(dy_f.transpose(1, 2), dy_ref) < 1.5e-2 and nerr(dy_u.transpose(1, 2), dy_ref) < 1.5e-2
+    assert nerr(dg_f, sgx) < 1e-2 and nerr(db_f, sg) < 1e-2
+    assert nerr(dy_f.transpose(1, 2), dy_ref) < 1.2 * nerr(dy_u.transpose(1, 2), dy_ref) + 1e-3
