@@ -179,7 +179,7 @@ __device__ __forceinline__ F8 unpack8(const Raw8<__nv_bfloat16>& r) {
 
 // MODE 0: sum,sumsq of x ; MODE 1: bn+gelu backward reduce over g = du * gelu'(bn(y)) (g is not stored:
 // the apply pass recomputes it, which is cheaper than a 59 MB write + read)
-template <typename T, int MODE, bool REVERSE = false>
+template <typename T, int MODE, bool REVERSE = false, bool STORE_G = false>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3)
 colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ ss, double* __restrict__ out,
                  int64_t rows, int Cp) {
@@ -216,11 +216,18 @@ colreduce_kernel(T* __restrict__ x, const T* __restrict__ y, const float* __rest
         for (int i = 0; i < 8; ++i) { a.v[i] += v.v[i]; q.v[i] += v.v[i] * v.v[i]; }
       } else {
         const F8 yy = unpack8(ry_[u]);
+        F8 gs;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float g = v.v[i] * gelu_grad_t<T>(fmaf(yy.v[i], sc.v[i], sh.v[i]));
+          if (STORE_G) g = to_f<T>(from_f<T>(g));   // the sums are those of g exactly as stored
+          gs.v[i] = g;
           a.v[i] += g;
           q.v[i] = fmaf(g, yy.v[i], q.v[i]);        // sum g*y; sum g*xhat = invstd*(sum g*y - mean*sum g) is formed in fp64 later
+        }
+        if (STORE_G) {   // g replaces du in place: the apply pass then needs no second GELU-derivative evaluation
+          const int64_t rm = REVERSE ? r1 - 1 - rr : rr;
+          st8<T>(x + rm * Cp + c, gs);
         }
       }
     }
@@ -623,11 +630,20 @@ int sd_bn_gelu_bwd_reduce(void* du_g, const void* y, const float* ss, double* re
   // Walk order of the two BatchNorm-backward passes (A/B switch SD_B200_BN_ORDER = ff | fr | rf): du was just written front
   // to back by the data-gradient conv, so its tail is what the L2 still holds
   if (bn_order()[0] == 'r') {
-    DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1, true><<<persistent_grid(rows, 4 * block.y, 3), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
+    DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1, true, false><<<persistent_grid(rows, 4 * block.y, 3), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
   } else {
     DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1, false><<<persistent_grid(rows, 4 * block.y, 3), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
   }
   return check_launch("bn_gelu_bwd_reduce");
+}
+
+int sd_bn_gelu_bwd_reduce_g(void* du_g, const void* y, const float* ss, double* red, int64_t rows, int Cp, int dtype,
+                            void* stream) {
+  SD_REQUIRE(Cp % 8 == 0 && Cp <= 2048, "sd_bn_gelu_bwd_reduce_g: bad Cp");
+  dim3 block(Cp / 8, chan_block_rows(Cp));
+  const size_t smem = (size_t)2 * block.y * Cp * sizeof(float);
+  DISPATCH_DTYPE(dtype, colreduce_kernel<T, 1, false, true><<<persistent_grid(rows, 4 * block.y, 3), block, smem, (cudaStream_t)stream>>>((T*)du_g, (const T*)y, ss, red, rows, Cp));
+  return check_launch("bn_gelu_bwd_reduce_g");
 }
 
 int sd_bn_bwd_apply(void* g_dy, const void* y, const float* ss, const double* red, float* dgamma, float* dbeta,

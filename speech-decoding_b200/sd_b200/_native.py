@@ -64,6 +64,7 @@ SIGNATURES = {
     "sd_bn_finalize": [vp, i32, i32, i64, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp],
     "sd_bn_gelu_fwd": [vp, vp, vp, i64, i32, i32, vp],
     "sd_bn_gelu_bwd_reduce": [vp, vp, vp, vp, i64, i32, i32, vp],
+    "sd_bn_gelu_bwd_reduce_g": [vp, vp, vp, vp, i64, i32, i32, vp],
     "sd_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, i64, i64, f32, i32, i32, i32, i32, vp],
     "sd_bn_bwd_apply_g": [vp, vp, vp, vp, vp, vp, i64, i64, f32, i32, i32, i32, i32, vp],
     "sd_glu_fwd": [vp, vp, i64, i32, i32, i32, i32, vp],

@@ -194,7 +194,14 @@ def bn_bwd_fusable(y):
     return y.dtype == torch.bfloat16 and get_impl() != "simt" and _BNR_FUSE
 
 
-_BNR_FUSE = os.environ.get("SD_B200_BNR_FUSE", "1") != "0"
+# Three ways to run the BatchNorm backward, measured at cfg2 on one B200 (same build, same box, 30 steps):
+#   stand-alone reduce + apply passes (default)                              6.795 ms/step, conv kernel 914 TFLOP/s
+#   reduce fused into the producing conv's epilogue (SD_B200_BNR_FUSE=1)      6.757 ms/step, conv kernel 827 TFLOP/s
+#   stand-alone reduce that stores g, apply without gelu' (SD_B200_BN_STORE_G=1)  6.98 ms/step
+# The fused epilogue removes a 35 us pass per BatchNorm but costs its conv 23 us: epilogue work is not free next to the
+# MMAs (shared-memory traffic, issue slots).  0.5 % is not worth a 10 % slower conv kernel, so it stays opt-in (and tested).
+_BNR_FUSE = os.environ.get("SD_B200_BNR_FUSE", "0") == "1"
+_BN_STORE_G = os.environ.get("SD_B200_BN_STORE_G", "0") == "1"
 
 
 def bn_gelu_bwd(du, y, ss, red, dgamma, dbeta, C, training, group=None, g_ready=False):
@@ -204,7 +211,11 @@ def bn_gelu_bwd(du, y, ss, red, dgamma, dbeta, C, training, group=None, g_ready=
     rows, Cp = y.shape[0] * y.shape[1], y.shape[2]
     n_stat, dscale = rows, 1.0
     if not g_ready:
-        nat.call("sd_bn_gelu_bwd_reduce", _p(du), _p(y), _p(ss), _p(red), rows, Cp, code_of(y), _st())
+        if _BN_STORE_G:      # the reduce pass leaves g in place of du, the apply pass does not recompute the GELU derivative
+            nat.call("sd_bn_gelu_bwd_reduce_g", _p(du), _p(y), _p(ss), _p(red), rows, Cp, code_of(y), _st())
+            g_ready = True
+        else:
+            nat.call("sd_bn_gelu_bwd_reduce", _p(du), _p(y), _p(ss), _p(red), rows, Cp, code_of(y), _st())
     if group is not None and training:
         import torch.distributed as dist
         from . import dist as sd_dist
