@@ -27,14 +27,18 @@ int check_launch(const char* what) {
 int current_impl() { return g_impl; }
 
 static int g_sm_limit = 0;   // 0 = no cap
+int device_sm_count() {       // of the CURRENT device (cached per device ordinal)
+  static int cache[SD_MAX_DEVICES];
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < SD_MAX_DEVICES && cache[dev] > 0) return cache[dev];
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < SD_MAX_DEVICES) cache[dev] = n;
+  return n;
+}
 int sm_budget() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  const int n = device_sm_count();
   return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 void set_sm_limit(int v) { g_sm_limit = v; }

@@ -371,11 +371,10 @@ int clip_dots_tc(const void* x, const void* z, float* dots, float* workspace, in
   CUtensorMap tx, tz;
   if (make_tmap_3d(&tx, dt, x, (uint64_t)D, (uint64_t)M, 1, (uint64_t)D * esz, (uint64_t)D * esz * M, kb_elems, 128, 1)) return 1;
   if (make_tmap_3d(&tz, dt, z, (uint64_t)D, (uint64_t)N, 1, (uint64_t)D * esz, (uint64_t)D * esz * N, kb_elems, (uint32_t)p.block_n, 1)) return 1;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[SD_MAX_DEVICES];
+  if (first_use_on_device(attr)) {
     SD_CUDA(cudaFuncSetAttribute(clip_dots_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     SD_CUDA(cudaFuncSetAttribute(clip_dots_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr = true;
   }
   const int smem = D_STAGES * D_STAGE_BYTES + 256 + 1024;
   if (bf16) clip_dots_tc_kernel<true><<<p.m_pairs * p.n_tiles * p.nsplit, NUM_THREADS, smem, st>>>(tx, tz, p);
@@ -406,11 +405,10 @@ int clip_dz_tc(const void* coef_t, const float* cz, const void* x, const float* 
     if (make_tmap_3d(&tc_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, coef_t, (uint64_t)M, (uint64_t)N, 1, (uint64_t)Mp * 4, (uint64_t)Mp * 4 * N, Z_BK, Z_BM, 1)) return 1;
     if (make_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, (uint64_t)D, (uint64_t)M, 1, (uint64_t)D * 4, (uint64_t)D * 4 * M, 32, Z_BK, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
   }
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[SD_MAX_DEVICES];
+  if (first_use_on_device(attr)) {
     SD_CUDA(cudaFuncSetAttribute(clip_dz_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     SD_CUDA(cudaFuncSetAttribute(clip_dz_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr = true;
   }
   const int smem = Z_STAGES * Z_STAGE_BYTES + Z_BM * Z_PITCH + 256 + 1024;
   const int grid = p.num_tiles < sms() ? p.num_tiles : sms();

@@ -33,6 +33,18 @@ int check_launch(const char* what);
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Per-DEVICE once-flags: cudaFuncSetAttribute (and occupancy queries) apply to the current device only, so a process that
+// drives several GPUs must repeat them on each.  `flags` is a static array of SD_MAX_DEVICES bools at the call site.
+constexpr int SD_MAX_DEVICES = 64;
+static inline bool first_use_on_device(bool* flags) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= SD_MAX_DEVICES) return true;     // out of table: just redo the (idempotent) set-up every time
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 // ---- dtype helpers --------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
@@ -168,6 +180,7 @@ int current_impl();
 // (data-parallel runs leave a few SMs to the concurrent NCCL kernels: a persistent grid that does not fit is
 // serialised into two waves by the first SM a collective holds).
 int sm_budget();
+int device_sm_count();
 void set_sm_limit(int v);
 
 // ---- per-family entry points (defined in the .cu files) ------------------------------------------

@@ -985,17 +985,21 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
       {conv_fwd_tc_kernel<false, false, 1>, conv_fwd_tc_kernel<false, false, 3>},
       {conv_fwd_tc_kernel<true, false, 1>, conv_fwd_tc_kernel<true, false, 3>},
       {conv_fwd_tc_kernel<true, true, 1>, conv_fwd_tc_kernel<true, true, 3>}};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SD_MAX_DEVICES];
+  if (first_use_on_device(attr_set)) {
     for (int m = 0; m < 3; ++m)
       for (int t = 0; t < 2; ++t)
         SD_CUDA(cudaFuncSetAttribute(kernels[m][t], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
   }
   const KernelFn kernel = kernels[mode][a.taps == 3];
   if (pair) {
     int grid = 2 * (p.num_tiles < n_pairs ? p.num_tiles : n_pairs);
-    static int max_pairs = -1;
+    static int max_pairs_dev[SD_MAX_DEVICES];
+    static bool max_pairs_known[SD_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool cacheable = dev >= 0 && dev < SD_MAX_DEVICES;
+    int max_pairs = cacheable && max_pairs_known[dev] ? max_pairs_dev[dev] : -1;
     if (max_pairs < 0) {   // all pairs must be co-resident: the tile walk is statically strided
       cudaLaunchConfig_t q;
       memset(&q, 0, sizeof(q));
@@ -1005,6 +1009,7 @@ int conv_fwd_tc(const sd_conv_args& a, cudaStream_t st) {
       attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
       q.attrs = &attr; q.numAttrs = 1;
       SD_CUDA(cudaOccupancyMaxActiveClusters(&max_pairs, kernels[1][1], &q));
+      if (cacheable) { max_pairs_dev[dev] = max_pairs; max_pairs_known[dev] = true; }
     }
     if (2 * max_pairs < grid) grid = 2 * max_pairs;
     SD_REQUIRE(grid >= 2 && (mode != 2 || grid / 2 >= p.n_tiles), "conv_fwd_tc: not enough resident CTA pairs (%d)", grid / 2);

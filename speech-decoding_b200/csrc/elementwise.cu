@@ -506,13 +506,7 @@ static inline int ew_grid(int64_t n, int threads) {
 // rows handled concurrently by one block of the channel-vector kernels (blockDim = (Cp/8, rows))
 // grid of the persistent channel kernels: every SM holds `per_sm` blocks, never more blocks than row groups
 static inline int persistent_grid(int64_t rows, int rows_per_iter, int per_sm) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   const int64_t groups = (rows + rows_per_iter - 1) / rows_per_iter;
   const int64_t g = (int64_t)sms * per_sm;
   return (int)(groups < g ? (groups > 0 ? groups : 1) : g);

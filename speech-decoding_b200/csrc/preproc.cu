@@ -186,10 +186,9 @@ extern "C" int sd_collate_preproc(const float* x, float* out, int64_t rows, int 
   int P = 2;
   while (P < T) P <<= 1;
   const size_t smem = (size_t)ROWS_PER_BLOCK * P * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SD_MAX_DEVICES];
+  if (first_use_on_device(attr_set)) {
     SD_CUDA(cudaFuncSetAttribute(collate_preproc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_PER_BLOCK * 2048 * 4));
-    attr_set = true;
   }
   if (T <= 512)     // register-resident sort (cfg1-cfg4: T = 360)
     collate_preproc_reg_kernel<<<(unsigned)cdiv(rows, ROWS_PER_BLOCK), ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(

@@ -559,10 +559,9 @@ static int conv_wgrad3_tc(const sd_wgrad_args& a, void* ws, size_t ws_bytes, cud
   if (make_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, (uint64_t)a.Kp, (uint64_t)a.T, (uint64_t)a.B,
                    (uint64_t)a.Kp * 2, (uint64_t)a.T * a.Kp * 2, 64, (uint32_t)(BLOCK_T + 2 * a.dil), 1))
     return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SD_MAX_DEVICES];
+  if (first_use_on_device(attr_set)) {
     SD_CUDA(cudaFuncSetAttribute(conv_wgrad3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
   }
   size_t bias_off = 0;
   const size_t need = ws_plan(nsplit, 3, p.n_tiles, p.c_tiles, p.block_c, a.dbias != nullptr, &bias_off);
@@ -634,10 +633,9 @@ int conv_wgrad_tc(const sd_wgrad_args& a, cudaStream_t st) {
   if (make_tmap_3d(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, (uint64_t)a.Kp, (uint64_t)a.T, (uint64_t)a.B,
                    (uint64_t)a.Kp * 2, (uint64_t)a.T * a.Kp * 2, 64, BLOCK_T, 1))
     return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SD_MAX_DEVICES];
+  if (first_use_on_device(attr_set)) {
     SD_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
   }
   size_t bias_off = 0;
   const size_t need = ws_plan(nsplit, a.taps, p.n_tiles, p.c_tiles, p.block_c, a.dbias != nullptr, &bias_off);
