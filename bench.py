@@ -118,8 +118,23 @@ def conv_traffic():
         return None
 
 
+class _Args(dict):
+    """the attribute-and-item config object the constructors read (models.py:22-43,93-95,173-178; loss.py:32,36)"""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+
+def make_args(D1, D2, F_, K, num_subjects, num_channels, last4layers, layout_seed=0):
+    return _Args(D1=D1, D2=D2, F=F_, K=K, d_drop=0.1, num_subjects=num_subjects, dataset="Gwilliams2022", root_dir="/nonexistent",
+                 num_channels=num_channels, preprocs={"last4layers": last4layers}, reduction="mean", init_temperature=5.1,
+                 layout_seed=layout_seed)          # layout_seed: explicit opt-in to the synthetic sensor layout
+
+
 def make_args_ns():
-    from oracle.restate import make_args
     return make_args(D1=CFG["D1"], D2=CFG["D2"], F_=CFG["F"], K=CFG["K"], num_subjects=CFG["S"],
                      num_channels=CFG["C"], last4layers=True)
 
@@ -279,6 +294,65 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+def dp_self_check(rank, world, dev):
+    """N > 1, before the timed run: the batch-sharded step (SyncBN on, fp32 mode, peer-memory exchanges) against the SAME
+    global batch run single-process on this rank's GPU through the same kernels -- loss and every parameter gradient.
+    (Single-GPU parity with the reference is what tests/ establish; this shows on the benchmark box that sharding does
+    not change the result.)  Small shapes, ~2 s.  Returns a dict for config.data_parallel.self_check."""
+    import torch.distributed as dist
+    import sd_b200
+    from sd_b200.dist import DataParallel
+    from speech_decoding.models import BrainEncoder
+    from speech_decoding.utils.loss import CLIPLoss
+    prev = sd_b200.get_precision()
+    try:
+        sd_b200.set_precision("fp32")
+        args = make_args(D1=40, D2=48, F_=64, K=4, num_subjects=6, num_channels=20, last4layers=False)
+        B, C, T = 12, 20, 96
+        g = torch.Generator().manual_seed(4242)
+        Xg = torch.randn(world * B, C, T, generator=g).clamp(-20, 20).to(dev)
+        Yg = torch.randn(world * B, 64, T, generator=g).to(dev)
+        idg = torch.randint(0, 5, (world * B,), generator=g, dtype=torch.int32)
+        nets = []
+        for _ in range(2):
+            torch.manual_seed(7)
+            nets.append((BrainEncoder(args).to(dev).train(), CLIPLoss(args).to(dev).train()))
+        (enc_dp, crit_dp), (enc_1, crit_1) = nets
+        dpc = DataParallel(enc_dp, crit_dp, sync_bn=True)
+        st = np.random.get_state()
+        sl = slice(rank * B, (rank + 1) * B)
+        loss_dp = crit_dp(Yg[sl], enc_dp(Xg[sl], idg[sl]))
+        loss_dp.backward()
+        np.random.set_state(st)                      # same spatial-dropout centre
+        loss_1 = crit_1(Yg, enc_1(Xg, idg))
+        loss_1.backward()
+        np.random.set_state(st)
+        worst, name, problem = 0.0, "", None
+        for (k, p), (_, q) in zip(enc_dp.named_parameters(), enc_1.named_parameters()):
+            if q.grad is None or p.grad is None:
+                if (q.grad is None) != (p.grad is None):      # (no early return: every rank must reach the collectives below)
+                    problem = "gradient presence differs for " + k
+                continue
+            a_, b_ = (torch.view_as_real(t) if t.is_complex() else t for t in (p.grad, q.grad))
+            e = float((a_ - b_).abs().max() / b_.abs().max().clamp_min(1e-30))
+            if e > worst:
+                worst, name = e, k
+        el = abs(float(loss_dp.detach()) - float(loss_1.detach())) / abs(float(loss_1.detach()))
+        out = {"ok": bool(el < 1e-4 and worst < 1e-4 and problem is None), "loss_rel_err": el, "worst_grad_rel_err": worst,
+               "worst_param": name, **({"problem": problem} if problem else {}),
+               "what": "fp32 mode, SyncBN, %d ranks x B=%d vs the same global batch on one GPU" % (world, B)}
+        t = torch.tensor([0.0 if out["ok"] else 1.0], device=dev)
+        dist.all_reduce(t)
+        out["ok_all_ranks"] = bool(float(t[0]) == 0.0)
+        dpc.close()
+        return out
+    except Exception as e:                      # never take the benchmark down
+        return {"ok": False, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    finally:
+        sd_b200.set_precision(prev)
+        torch.cuda.empty_cache()
+
+
 def run_ours(a, rank, world, local_rank):
     import torch.distributed as dist
     import sd_b200
@@ -289,6 +363,7 @@ def run_ours(a, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    self_check = dp_self_check(rank, world, dev) if world > 1 and a.dp_check else None
     sd_b200.set_precision(a.precision)
     torch.manual_seed(0)           # identical replicas on every rank
     np.random.seed(0)              # identical dropout centres on every rank
@@ -519,7 +594,7 @@ def run_ours(a, rank, world, local_rank):
             "speech_row_gather_schedule": "next step's rows, during this step's backward" if pipelined else "this step's rows, during the encoder forward",
             "small_exchanges": "one-kernel all-gather through peer memory (sd_peer_exchange)" if dp.mailbox is not None else "NCCL all-reduce",
             "grad_allreduce_launches_per_step": round(red.launched / max(1, steps_seen[0]), 2),
-            "numa_bound_cpus": numa_cpus}
+            "numa_bound_cpus": numa_cpus, "self_check": self_check}
     if roof:
         line["roofline"] = roof
     if world == 1 and not a.no_cpu:
@@ -538,6 +613,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3", "fp32"])
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--sync-bn", type=int, default=0)
+    ap.add_argument("--dp-check", type=int, default=1, help="N>1: sharded step vs the global batch on one GPU before the timed run")
     ap.add_argument("--dp-push-at", type=int, default=-1,
                     help="pipelined gather: start the pushes after the k-th stage from the end of backward (-1: right after the loss forward)")
     ap.add_argument("--dp-pipeline", type=int, default=1,

@@ -88,12 +88,19 @@ class PeerGather:
         self.consts = torch.arange(1, self.NCONST + 1, dtype=torch.int32, device=self.device)    # flag values to copy from
         self.timing = None           # tools/dist_phases.py: list of (start, end) timing events of the pushes, per call
 
-    def _release(self):
+    def _release(self, collective=False):
+        """Unmap the peers' buffers, then free the own one.  An exporter must not free memory an importer still has
+        mapped, so when every rank releases together (re-allocation for a new shape, DataParallel.close) a host barrier
+        separates the two halves; a lone release (object finalisation at process teardown) just lets go."""
         from . import _native as nat
+        had = self.base is not None
         if self.peers is not None:
             for r, p in enumerate(self.peers):
                 if r != self.rank and p:
                     nat.call("sd_ipc_close_handle", p)
+        if collective and had:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.host_group)
         if self.base:
             nat.call("sd_peer_free", self.base)
         self.base = self.peers = self.shape = None
@@ -102,7 +109,7 @@ class PeerGather:
         import ctypes
         from . import _native as nat
         torch.cuda.synchronize(self.device)
-        self._release()
+        self._release(collective=True)       # (every rank re-allocates at the same step: the shard shape changed everywhere)
         self.rows_bytes = self.world * rows * D * 2
         self.norm_off = (self.rows_bytes + 255) // 256 * 256
         self.flag_off = self.norm_off + (self.world * rows * 4 + 255) // 256 * 256
@@ -196,7 +203,7 @@ class PeerMailbox:
     def __init__(self, group, host_group, device):
         import ctypes
         from . import _native as nat
-        self.group, self.device = group, torch.device(device)
+        self.group, self.host_group, self.device = group, host_group, torch.device(device)
         self.world, self.rank = world_rank(group)
         self.epoch = 0
         nbytes = 2 * self.world * self.CAP + 256
@@ -244,13 +251,23 @@ class PeerMailbox:
                      torch.cuda.current_stream().cuda_stream)
         return t
 
+    def close(self, collective=False):
+        """see PeerGather._release"""
+        from . import _native as nat
+        if self.base is None:
+            return
+        for r, p in enumerate(self.peers):
+            if r != self.rank and p:
+                nat.call("sd_ipc_close_handle", p)
+        if collective:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.host_group)
+        nat.call("sd_peer_free", self.base)
+        self.base, self.peers = None, []
+
     def __del__(self):
         try:
-            from . import _native as nat
-            for r, p in enumerate(self.peers):
-                if r != self.rank and p:
-                    nat.call("sd_ipc_close_handle", p)
-            nat.call("sd_peer_free", self.base)
+            self.close()
         except Exception:
             pass
 
@@ -477,6 +494,20 @@ class DataParallel:
             except Exception as e:                                  # pragma: no cover
                 import warnings
                 warnings.warn("sd_b200: copy-engine peer gather unavailable (%s); using the NCCL all-gather" % e)
+
+    def close(self):
+        """Collective: release the peer-memory buffers (every rank must call it) and detach from the modules."""
+        if self.peer is not None:
+            self.peer._release(collective=True)
+            _PEER_GATHER.pop(id(self.group), None)
+            self.peer = None
+        if self.mailbox is not None:
+            self.mailbox.close(collective=True)
+            _MAILBOX.pop(id(self.group), None)
+            self.mailbox = None
+        self.pipe.reducer = None
+        self.pipe.bn_group = self.pipe.host_group = None
+        self.loss_fn.process_group = None
 
     def prefetch_targets(self, Y, during_backward=None):
         """Start the all-gather of the speech embeddings for the coming step NOW (they are input data, known
