@@ -305,8 +305,10 @@ def dp_self_check(rank, world, dev):
     from speech_decoding.models import BrainEncoder
     from speech_decoding.utils.loss import CLIPLoss
     prev = sd_b200.get_precision()
+    rng_state = np.random.get_state()
     try:
         sd_b200.set_precision("fp32")
+        np.random.seed(4242)             # the same spatial-dropout centre on every rank (models.py:81 draws from numpy's RNG)
         args = make_args(D1=40, D2=48, F_=64, K=4, num_subjects=6, num_channels=20, last4layers=False)
         B, C, T = 12, 20, 96
         g = torch.Generator().manual_seed(4242)
@@ -350,6 +352,7 @@ def dp_self_check(rank, world, dev):
         return {"ok": False, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     finally:
         sd_b200.set_precision(prev)
+        np.random.set_state(rng_state)
         torch.cuda.empty_cache()
 
 
