@@ -363,6 +363,7 @@ def run_ours(a, rank, world, local_rank):
     from speech_decoding.models import BrainEncoder
     from speech_decoding.utils.loss import CLIPLoss
 
+    os.environ.setdefault("SD_B200_STRICT_TC", "1")     # a bf16 launch that cannot run on the tcgen05 kernels is an error here
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None

@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, device query, implementation dispatch for the conv family.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -67,6 +68,14 @@ static int warn_simt_fallback(const char* what, int N, int K, int taps, int act,
                   "CUDA-core kernel (~10x slower)\n", what, N, K, taps, act, out_mode);
   return 0;
 }
+static bool strict_tc() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SD_B200_STRICT_TC");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0;
+}
 
 }  // namespace sd
 
@@ -121,7 +130,11 @@ int sd_conv_fwd(const sd_conv_args* a, void* stream) {
     return conv_fwd_tc(*a, (cudaStream_t)stream);
   }
   if (impl == SD_IMPL_AUTO && conv_fwd_tc_supported(*a)) return conv_fwd_tc(*a, (cudaStream_t)stream);
-  if (a->dtype == SD_BF16 && impl == SD_IMPL_AUTO) warn_simt_fallback("sd_conv_fwd", a->N, a->K, a->taps, a->act, a->out_mode);
+  if (a->dtype == SD_BF16 && impl == SD_IMPL_AUTO) {
+    SD_REQUIRE(!strict_tc(), "sd_conv_fwd: bf16 configuration (N=%d K=%d taps=%d act=%d out=%d) not supported by the tcgen05 kernels "
+               "(SD_B200_STRICT_TC=1)", a->N, a->K, a->taps, a->act, a->out_mode);
+    warn_simt_fallback("sd_conv_fwd", a->N, a->K, a->taps, a->act, a->out_mode);
+  }
   return conv_fwd_simt(*a, (cudaStream_t)stream);
 }
 
@@ -141,7 +154,11 @@ int sd_conv_wgrad(const sd_wgrad_args* a, void* stream) {
     return conv_wgrad_tc(*a, (cudaStream_t)stream);
   }
   if (impl == SD_IMPL_AUTO && conv_wgrad_tc_supported(*a)) return conv_wgrad_tc(*a, (cudaStream_t)stream);
-  if (a->dtype == SD_BF16 && impl == SD_IMPL_AUTO) warn_simt_fallback("sd_conv_wgrad", a->N, a->K, a->taps, 0, 0);
+  if (a->dtype == SD_BF16 && impl == SD_IMPL_AUTO) {
+    SD_REQUIRE(!strict_tc(), "sd_conv_wgrad: bf16 configuration (N=%d K=%d taps=%d) not supported by the tcgen05 kernels "
+               "(SD_B200_STRICT_TC=1)", a->N, a->K, a->taps);
+    warn_simt_fallback("sd_conv_wgrad", a->N, a->K, a->taps, 0, 0);
+  }
   return conv_wgrad_simt(*a, (cudaStream_t)stream);
 }
 
