@@ -232,6 +232,7 @@ def gpu_eager_rate(dev, B, steps=3, warmup=1):
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
+    ref = None
     try:
         ref = ReferenceStep(dev)
         X, Y, ids = ref.data(B)
@@ -601,6 +602,14 @@ def run_ours(a, rank, world, local_rank):
             "numa_bound_cpus": numa_cpus, "self_check": self_check}
     if roof:
         line["roofline"] = roof
+    if world == 1 and not a.no_eager:
+        # second stated baseline: the reference's own modules, stock PyTorch eager (cuDNN / cuBLAS, TF32 on) on THIS GPU
+        try:
+            del enc, crit, opt, graphed
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_rate(dev, B)
+        except Exception as e:
+            line["gpu_eager_baseline"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:160])}
     if world == 1 and not a.no_cpu:
         r = cpu_reference_rate(2, 1, 64)
         line["cpu_baseline"] = {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
@@ -630,6 +639,7 @@ def main():
     ap.add_argument("--window", type=int, default=CFG["T"],
                     help="samples per window: 360 = 3 s (cfg2/cfg3), 1200 = 10 s (BASELINE.json configs[4])")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the stock-PyTorch-eager-on-this-GPU baseline")
     a = ap.parse_args()
     CFG["T"] = a.window
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
